@@ -1,0 +1,129 @@
+/* pysp_b200 -- C ABI of the B200-native develop path (libpysp_b200.so).
+ *
+ * Drop-in boundary for bullbin/pySP's raw -> linear-sRGB develop path.  The reference has no FFI of its
+ * own: the seams are Python callables plus one Cython `cpdef`.  Each entry point
+ * below names the reference callable(s) it replaces (file:line in the reference tree); INTEGRATION.md
+ * shows the ctypes binding a pySP maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; every image pointer is a DEVICE pointer owned by the caller (e.g. a torch
+ *    tensor's data_ptr()) unless the name ends in `_host`;
+ *  - asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to void*; NULL = default
+ *    stream) on the current device; the library allocates nothing and keeps no mutable global state
+ *    (scratch is caller-provided), so calls are re-entrant across streams, devices and threads;
+ *  - return value: PYSP_OK or a negative code; pysp_last_error() returns the calling thread's message.
+ *    PYSP_ERR_INVALID maps to the reference's ValueError/AssertionError cases, PYSP_ERR_UNSUPPORTED to
+ *    NotImplementedError (image.py:152,176), PYSP_ERR_CUDA to a CUDA runtime failure;
+ *  - there is no CPU path: without a CUDA device every compute entry point fails with PYSP_ERR_CUDA.
+ */
+#ifndef PYSP_B200_H
+#define PYSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYSP_OK 0
+#define PYSP_ERR_INVALID (-1)
+#define PYSP_ERR_UNSUPPORTED (-2)
+#define PYSP_ERR_CUDA (-3)
+
+/* base_types/image_base.py:13-17 (BayerPattern) */
+#define PYSP_CFA_RGGB 1
+#define PYSP_CFA_BGGR 2
+#define PYSP_CFA_GRBG 3
+#define PYSP_CFA_GBRG 4
+
+#define PYSP_IN_U16 0      /* sensor counts; normalisation (normalization.py:4-25) is fused into the load */
+#define PYSP_IN_F32 1      /* `sensor_scaled` float32 mosaic (RawRggbBayerData, HDR mosaics) */
+
+#define PYSP_OUT_CAM_F32 0 /* RawDemosaicData.image: camera RGB, WB applied once (debayer/ahd.py:167) */
+#define PYSP_OUT_LIN_F32 1 /* ... .to_lin_srgb() (base_types/image_base.py:62-64) */
+#define PYSP_OUT_LIN_F16 2 /* same, stored as half */
+
+#define PYSP_MAX_BRACKETS 16
+
+/* One develop call = RawBayerData.demosaic(QualityDemosaic.Best, stages) [+ .to_lin_srgb()
+ * [+ lin_srgb_to_srgb]] on one frame or one row band of it.
+ * Replaces: image.py:191-197 (to_rggb, demosaic), image.py:156-183 (dispatch, un-flip),
+ * debayer/ahd.py:14-170 (debayer_ahd incl. the Cython build_map, ahd_homogeneity_cython.pyx:61),
+ * normalization.py:4-25 when in_kind == PYSP_IN_U16, base_types/image_base.py:62-64 and
+ * colorize/transform.py:21-53,76-99 for the PYSP_OUT_LIN_* kinds. */
+typedef struct pysp_develop_args {
+    int32_t height, width;       /* whole frame, both even and >= 4 */
+    int32_t cfa_pattern;         /* PYSP_CFA_*; non-RGGB frames are flipped on load/store (image.py:143-152) */
+    int32_t in_kind;             /* PYSP_IN_* */
+    const void* in;              /* rows [in_row0, in_row0 + in_rows) of the frame as stored */
+    int64_t in_pitch_bytes;
+    int32_t in_row0, in_rows;
+    float black[4];              /* per CFA site of the STORED mosaic, reference order [TL, TR, BR, BL] */
+    float white[4];              /*   (normalization.py:20-23); ignored for PYSP_IN_F32 */
+    float wb[3];                 /* cam_wb.get_reciprocal_multipliers() (wb_cct/cam_wb.py:236-243), float32 */
+    double cam_to_srgb[9];       /* row-major 3x3 of colorize/transform.py:40-49, built on the host in float64 */
+    int32_t stages;              /* postprocess_stages, clamped at 0 (debayer/ahd.py:163) */
+    int32_t is_hdr;              /* image.get_hdr() (debayer/ahd.py:52-59) */
+    int32_t apply_gamma;         /* fuse lin_srgb_to_srgb (colorize/transform.py:89-99) into the epilogue */
+    int32_t out_kind;            /* PYSP_OUT_* */
+    void* out;                   /* [rows][width][3], rows [out_row0, ...) of the frame as stored */
+    int64_t out_pitch_bytes;
+    int32_t out_row0;
+    int32_t row_begin, row_end;  /* stored rows to produce, even; whole frame = [0, height) */
+    void* scratch;               /* >= pysp_develop_scratch_bytes(...) bytes when stages > 0 */
+    int64_t scratch_bytes;
+    const void* lab_lut;         /* device copy of the table packed by pysp_lab_lut_pack_host */
+} pysp_develop_args;
+
+int pysp_develop(const pysp_develop_args* args, void* stream);
+
+/* Bytes of device scratch pysp_develop needs for a band of `rows` output rows (0 when stages <= 0). */
+int64_t pysp_develop_scratch_bytes(int32_t width, int32_t rows, int32_t stages);
+
+/* Rows of mosaic needed above/below a band: 6 + 4*stages (stencil reach). */
+int32_t pysp_develop_halo_rows(int32_t stages);
+
+/* cv2.cvtColor(COLOR_RGB2LAB) float32 table (debayer/ahd.py:58,62): pack int16 [33][33][33][3] (L,a,b)
+ * into the device layout (pysp_lab_lut_bytes() bytes); the caller uploads the result. */
+int64_t pysp_lab_lut_bytes(void);
+int pysp_lab_lut_pack_host(const int16_t* lut33_host, void* packed_host);
+
+/* bayer_normalize (normalization.py:4-25): u16 [H][W] -> float32 [H][W]; black/white in [TL,TR,BR,BL]. */
+int pysp_normalize_u16(const uint16_t* in, int64_t in_pitch_bytes, float* out, int64_t out_pitch_bytes,
+                       int32_t height, int32_t width, const float black[4], const float white[4],
+                       void* stream);
+
+/* cam_to_rgb_norm / cam_to_lin_srgb (colorize/transform.py:21-53,76-87): n_pixels RGB float32 ->
+ * float32 (or half when out_f16); `m` row-major float64; clip = clip_highlights. */
+int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n_pixels, const double m[9], int32_t clip,
+                         int32_t apply_gamma, int32_t out_f16, void* stream);
+
+/* lin_srgb_to_srgb (colorize/transform.py:89-99) on n float32 values. */
+int pysp_lin_srgb_to_srgb(const float* in, float* out, int64_t n_values, void* stream);
+
+/* fuse_exposures_to_raw (raw_hdr.py:85-158), arithmetic lines 108-148: n float32 RGGB mosaics ->
+ * HDR mosaic (+ optional int32 contribution count).  ev_offset[i] = float32(2**(ev_i - target_ev));
+ * bias[i*3+c] = 1.6**(-0.1*|ev_offset[i]*wb[c]|) evaluated by the host in float32 (it has three distinct
+ * values per bracket, so the device needs no pow).  Brackets are accumulated strictly in list order. */
+int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitch_bytes, int32_t height,
+                        int32_t width, const float* ev_offset, const float* bias, int32_t brightest,
+                        float* out, int64_t out_pitch_bytes, int32_t* count, int64_t count_pitch_bytes,
+                        void* stream);
+
+/* Bench instrumentation (no reference counterpart): when enabled, pysp_develop brackets each kernel launch
+ * with CUDA events on the launching stream; collect() synchronises them and returns, per kernel slot
+ * (0 = ahd_select_kernel, 1 = median_stage_kernel; 4 slots), the summed device milliseconds and launch
+ * count since the last enable/collect. */
+void pysp_timing_enable(int32_t on);
+int pysp_timing_collect(double total_ms[4], int64_t launches[4]);
+
+const char* pysp_last_error(void);
+const char* pysp_version(void);
+/* Number of kernels this library has launched in this process (for bench accounting). */
+int64_t pysp_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

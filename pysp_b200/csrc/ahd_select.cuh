@@ -1,0 +1,420 @@
+// K1: RGGB mosaic tile (+6 px halo) -> AHD direction-selected camera RGB (debayer/ahd.py:69-145).
+//
+// One CTA develops one TW x TH output tile entirely in shared memory:
+//   phase 0  load + normalise (normalization.py:20-25) + white balance (ahd.py:77-80) into four
+//            quarter-resolution CFA planes (bayer_chan_mixer.py:13-21 becomes index math);
+//   phase 1  5-tap H and V green at R/B sites (ahd.py:97-102) and colour differences;
+//   phase 2  per 2x2 quad and per direction: green high-pass (ahd.py:120-121), 4-phase Gaussian
+//            upsample of (c-g) and g (edge_assisted_gaussian.py:140-143), metric RGB in float64,
+//            cv2-Lab through the 33^3 table (ahd.py:45-62); Lab kept for the tile+2 px, the two
+//            candidate images for the tile only -- neither ever goes to HBM;
+//   phase 3  homogeneity counts (ahd_homogeneity_cython.pyx:36-58) for the tile+1 px;
+//   phase 4  3x3 box vote (ahd.py:133-139), select, epilogue, store.
+// All planes are stored phase-separated ("quarter planes") so that a thread that owns a 2x2 quad
+// addresses shared memory with unit stride and compile-time plane offsets.
+//
+// EDGE=true tiles (touching the frame border, or partial) apply the reference's six border rules by
+// index mapping; interior tiles compile to straight-line code.  Band seams are NOT borders: rows
+// outside [y_begin,y_end) but inside the frame are read from the buffer like any other halo.
+#pragma once
+#include "pysp_common.cuh"
+
+namespace pysp {
+
+template <int TW_, int TH_>
+struct SelectTile {
+    static constexpr int TW = TW_, TH = TH_;
+    static constexpr int QW = (TW + 12) / 2, QH = (TH + 12) / 2;   // quarter planes incl. 3-quad halo
+    static constexpr int QN = QW * QH;
+    static constexpr int LW = TW + 4, LH = TH + 4;                 // Lab region (tile + 2)
+    static constexpr int CW = TW + 2, CH = TH + 2;                 // count region (tile + 1)
+    // quarter planes (float): mosaic R,G1,G2,B ; H/V green at R and B ; H/V colour difference at R and B
+    enum { P_R = 0, P_G1, P_G2, P_B, P_GHR, P_GHB, P_GVR, P_GVB, P_DHR, P_DHB, P_DVR, P_DVB, NPLANES };
+    static constexpr int OFF_Q = 0;                                // floats
+    static constexpr int OFF_LABL = OFF_Q + NPLANES * QN;          // [2][LH][LW] float  L
+    static constexpr int OFF_LABAB = OFF_LABL + 2 * LH * LW;       // [2][LH][LW] u32    a|b<<16
+    static constexpr int OFF_CAND = OFF_LABAB + 2 * LH * LW;       // [4][TH][TW] float  RH,BH,RV,BV
+    static constexpr int OFF_CNT = OFF_CAND + 4 * TH * TW;         // [CH][CW] u8  cntH | cntV<<4
+    static constexpr int SMEM_BYTES = OFF_CNT * 4 + ((CH * CW + 15) / 16) * 16;
+    static_assert(TW % 2 == 0 && TH % 2 == 0, "tile must be quad aligned");
+};
+
+// ---- phase 0 ------------------------------------------------------------------------------------------
+PYSP_HD float load_site(const SelectParams& p, int y, int x) {
+    // (y,x): logical in-frame coordinate -> normalised, white-balanced photosite value
+    int sy = p.g.flip_y ? p.g.H - 1 - y : y;
+    int sx = p.g.flip_x ? p.g.W - 1 - x : x;
+    float s;
+    const char* row = (const char*)p.in + (long long)(sy - p.in_row0) * p.in_pitch;
+    if (p.in_kind == IN_U16) {
+        int pos = ((sy & 1) << 1) | (sx & 1);
+        float v = (float)pysp_ldg((const uint16_t*)row + sx);
+        float t = fminf(fmaxf(v - p.black[pos], 0.0f), p.white[pos]);
+        s = t / p.white[pos];
+    } else {
+        s = pysp_ldg((const float*)row + sx);
+    }
+    int ch = (y & 1) + (x & 1);                     // R:0  G:1  B:2
+    return s * p.c.wb[ch];
+}
+
+// 5 taps, strictly left to right (ahd.py:97-102)
+PYSP_HD float tap5(float a, float b, float c, float d, float e) {
+    return ((((a * PYSP_H0) + (b * PYSP_H1)) + (c * PYSP_H2)) + (d * PYSP_H1)) + (e * PYSP_H0);
+}
+
+// correlation accumulators for the four output phases of the 4-phase upsample; v[dy+1][dx+1] are the 3x3
+// quarter neighbours.  Taps in raster order; power-of-two weights are exact so fmaf == mul, add.
+// base TOP_LEFT (gaussian.py:19-53 with base R): outputs TL,TR,BL,BR of the quad
+PYSP_HD void up_tl(const float v[3][3], float o[4]) {
+    float a = v[0][0] * 0.015625f;
+    a = a + v[0][1] * 0.09375f;
+    a = fmaf(v[0][2], 0.015625f, a);
+    a = a + v[1][0] * 0.09375f;
+    a = a + v[1][1] * 0.5625f;
+    a = a + v[1][2] * 0.09375f;
+    a = fmaf(v[2][0], 0.015625f, a);
+    a = a + v[2][1] * 0.09375f;
+    a = fmaf(v[2][2], 0.015625f, a);
+    o[0] = a;
+    a = v[0][1] * 0.0625f;
+    a = fmaf(v[0][2], 0.0625f, a);
+    a = a + v[1][1] * 0.375f;
+    a = a + v[1][2] * 0.375f;
+    a = fmaf(v[2][1], 0.0625f, a);
+    a = fmaf(v[2][2], 0.0625f, a);
+    o[1] = a;
+    a = v[1][0] * 0.0625f;
+    a = a + v[1][1] * 0.375f;
+    a = fmaf(v[1][2], 0.0625f, a);
+    a = fmaf(v[2][0], 0.0625f, a);
+    a = a + v[2][1] * 0.375f;
+    a = fmaf(v[2][2], 0.0625f, a);
+    o[2] = a;
+    a = v[1][1] * 0.25f;
+    a = fmaf(v[1][2], 0.25f, a);
+    a = fmaf(v[2][1], 0.25f, a);
+    a = fmaf(v[2][2], 0.25f, a);
+    o[3] = a;
+}
+// base BOTTOM_RIGHT (base B)
+PYSP_HD void up_br(const float v[3][3], float o[4]) {
+    float a = v[0][0] * 0.25f;
+    a = fmaf(v[0][1], 0.25f, a);
+    a = fmaf(v[1][0], 0.25f, a);
+    a = fmaf(v[1][1], 0.25f, a);
+    o[0] = a;
+    a = v[0][0] * 0.0625f;
+    a = a + v[0][1] * 0.375f;
+    a = fmaf(v[0][2], 0.0625f, a);
+    a = fmaf(v[1][0], 0.0625f, a);
+    a = a + v[1][1] * 0.375f;
+    a = fmaf(v[1][2], 0.0625f, a);
+    o[1] = a;
+    a = v[0][0] * 0.0625f;
+    a = fmaf(v[0][1], 0.0625f, a);
+    a = a + v[1][0] * 0.375f;
+    a = a + v[1][1] * 0.375f;
+    a = fmaf(v[2][0], 0.0625f, a);
+    a = fmaf(v[2][1], 0.0625f, a);
+    o[2] = a;
+    a = v[0][0] * 0.015625f;
+    a = a + v[0][1] * 0.09375f;
+    a = fmaf(v[0][2], 0.015625f, a);
+    a = a + v[1][0] * 0.09375f;
+    a = a + v[1][1] * 0.5625f;
+    a = a + v[1][2] * 0.09375f;
+    a = fmaf(v[2][0], 0.015625f, a);
+    a = a + v[2][1] * 0.09375f;
+    a = fmaf(v[2][2], 0.015625f, a);
+    o[3] = a;
+}
+
+PYSP_HD float gauss_row(float l, float c, float r) { return (PYSP_GK1 * c) + (PYSP_GK0 * (l + r)); }
+
+template <int TW, int TH, bool EDGE>
+PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_x, int tile_y) {
+    typedef SelectTile<TW, TH> L;
+    constexpr int QW = L::QW, QH = L::QH, QN = L::QN;
+    const int H = p.g.H, W = p.g.W;
+    const int hq = H >> 1, wq = W >> 1;
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;     // logical origin of the output tile (even)
+    const int qx0 = (x0 >> 1) - 3, qy0 = (y0 >> 1) - 3;           // quarter-plane origin
+    float* Q = sm + L::OFF_Q;
+    float* labL = sm + L::OFF_LABL;
+    uint32_t* labAB = (uint32_t*)(sm + L::OFF_LABAB);
+    float* cand = sm + L::OFF_CAND;
+    uint8_t* cnt = (uint8_t*)(sm + L::OFF_CNT);
+
+    // ---------------- phase 0: load, normalise, white balance -> quarter planes --------------------------
+    PYSP_ITEMS(it, QN * 2) {
+        // one item = the two horizontally adjacent sites (even,odd column) of one mosaic row
+        int ly = it / QW, qx = it - ly * QW;          // ly: local full-res row 0..2*QH-1
+        int y = 2 * qy0 + ly, x = 2 * (qx0 + qx);
+        int yy = y, xa = x, xb = x + 1;
+        bool ok = true;
+        if (EDGE) {
+            yy = phase_clamp(y, H); xa = phase_clamp(x, W); xb = phase_clamp(x + 1, W);
+            // rows of the frame that this band's buffer does not hold are never consumed
+            int sy = p.g.flip_y ? H - 1 - yy : yy;
+            ok = sy >= p.in_row0 && sy < p.in_row1;
+        }
+        float va = 0.0f, vb = 0.0f;
+        if (ok) { va = load_site(p, yy, xa); vb = load_site(p, yy, xb); }
+        int qi = (ly >> 1) * QW + qx;
+        if (ly & 1) { Q[L::P_G2 * QN + qi] = va; Q[L::P_B * QN + qi] = vb; }
+        else        { Q[L::P_R * QN + qi] = va; Q[L::P_G1 * QN + qi] = vb; }
+    }
+    PYSP_SYNC();
+
+    // ---------------- phase 1: directional greens and colour differences at R/B sites ---------------------
+    {
+        constexpr int GW = QW - 2, GH = QH - 2;        // quads with a 2-quad halo
+        PYSP_ITEMS(it, GW * GH) {
+            int gy = it / GW, gx = it - gy * GW;
+            int i = gy + 1, j = gx + 1;                // local quarter index
+            if (EDGE) {
+                int fi = qy0 + i, fj = qx0 + j;
+                if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue;
+            }
+            int c = i * QW + j;
+            const float* R = Q + L::P_R * QN; const float* G1 = Q + L::P_G1 * QN;
+            const float* G2 = Q + L::P_G2 * QN; const float* B = Q + L::P_B * QN;
+            float r = R[c], b = B[c];
+            float ghr = tap5(R[c - 1], G1[c - 1], r, G1[c], R[c + 1]);
+            float gvr = tap5(R[c - QW], G2[c - QW], r, G2[c], R[c + QW]);
+            float ghb = tap5(B[c - 1], G2[c], b, G2[c + 1], B[c + 1]);
+            float gvb = tap5(B[c - QW], G1[c], b, G1[c + QW], B[c + QW]);
+            Q[L::P_GHR * QN + c] = ghr; Q[L::P_GVR * QN + c] = gvr;
+            Q[L::P_GHB * QN + c] = ghb; Q[L::P_GVB * QN + c] = gvb;
+            Q[L::P_DHR * QN + c] = r - ghr; Q[L::P_DVR * QN + c] = r - gvr;
+            Q[L::P_DHB * QN + c] = b - ghb; Q[L::P_DVB * QN + c] = b - gvb;
+        }
+    }
+    PYSP_SYNC();
+
+    // ---------------- phase 2: candidates + Lab per quad, both directions ----------------------------------
+    {
+        constexpr int PW = L::LW / 2, PH = L::LH / 2;  // quads of the Lab region (1-quad halo)
+        PYSP_ITEMS(it, PW * PH) {
+            int py = it / PW, px = it - py * PW;
+            int i = py + 2, j = px + 2;                // local quarter index
+            int fi = qy0 + i, fj = qx0 + j;            // frame quarter index
+            if (EDGE) { if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue; }
+            // local quarter row/col of the 3 neighbours under quarter-grid REFLECT_101
+            int ri[3], cj[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                ri[d] = EDGE ? reflect101(fi + d - 1, hq) - qy0 : i + d - 1;
+                cj[d] = EDGE ? reflect101(fj + d - 1, wq) - qx0 : j + d - 1;
+            }
+            const bool inner = py >= 1 && py <= TH / 2 && px >= 1 && px <= TW / 2;
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                const float* GR = Q + (dir ? L::P_GVR : L::P_GHR) * QN;
+                const float* GB = Q + (dir ? L::P_GVB : L::P_GHB) * QN;
+                const float* DR = Q + (dir ? L::P_DVR : L::P_DHR) * QN;
+                const float* DB = Q + (dir ? L::P_DVB : L::P_DHB) * QN;
+                const float* G1 = Q + L::P_G1 * QN;
+                const float* G2 = Q + L::P_G2 * QN;
+                float gr[3][3], gb[3][3], dr[3][3], db[3][3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        int c = ri[a] * QW + cj[b];
+                        gr[a][b] = GR[c]; gb[a][b] = GB[c]; dr[a][b] = DR[c]; db[a][b] = DB[c];
+                    }
+                // full-res green window rows 2i-1..2i+2, cols 2j-1..2j+2 for the high-pass, with full-res
+                // REFLECT_101 (ahd.py:120).  Reflection keeps the CFA phase, so the plane of every window
+                // cell is static; only its quarter index moves at the frame border.
+                float gw[4][4];
+                {
+                    // quarter indices of window rows/cols: row -1 -> odd row of quad i-1, rows 0,1 -> quad i,
+                    // row 2 -> even row of quad i+1
+                    int wr[4], wc[4];
+                    if (EDGE) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            wr[k] = (reflect101(2 * fi - 1 + k, H) >> 1) - qy0;
+                            wc[k] = (reflect101(2 * fj - 1 + k, W) >> 1) - qx0;
+                        }
+                    } else {
+                        wr[0] = i - 1; wr[1] = i; wr[2] = i; wr[3] = i + 1;
+                        wc[0] = j - 1; wc[1] = j; wc[2] = j; wc[3] = j + 1;
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            int c = wr[a] * QW + wc[b];
+                            const bool oddrow = (a & 1) == 0, oddcol = (b & 1) == 0;   // window starts at -1
+                            gw[a][b] = oddrow ? (oddcol ? GB[c] : G2[c]) : (oddcol ? G1[c] : GR[c]);
+                        }
+                }
+                float hf[4];
+                {
+                    float rp[4][2];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        rp[a][0] = gauss_row(gw[a][0], gw[a][1], gw[a][2]);
+                        rp[a][1] = gauss_row(gw[a][1], gw[a][2], gw[a][3]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+                            hf[a * 2 + b] = gw[a + 1][b + 1] - gauss_row(rp[a][b], rp[a + 1][b], rp[a + 2][b]);
+                }
+                float ugr[4], udr[4], ugb[4], udb[4];
+                up_tl(gr, ugr); up_tl(dr, udr); up_br(gb, ugb); up_br(db, udb);
+                float Rc[4], Gc[4], Bc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    Rc[k] = udr[k] + (ugr[k] + hf[k]);          // edge_assisted_gaussian.py:141-143
+                    Bc[k] = udb[k] + (ugb[k] + hf[k]);
+                    Gc[k] = gw[1 + (k >> 1)][1 + (k & 1)];
+                }
+                // Lab of the metric image, kept for the tile + 2 px
+                float* oL = labL + dir * (L::LH * L::LW);
+                uint32_t* oAB = labAB + dir * (L::LH * L::LW);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    LabQ q = metric_lab(p.c, p.lut, Rc[k], Gc[k], Bc[k]);
+                    int o = (2 * py + (k >> 1)) * L::LW + 2 * px + (k & 1);
+                    oL[o] = q.L; oAB[o] = q.ab;
+                }
+                if (inner) {
+                    float* oR = cand + (dir * 2 + 0) * (TH * TW);
+                    float* oB = cand + (dir * 2 + 1) * (TH * TW);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int o = (2 * (py - 1) + (k >> 1)) * TW + 2 * (px - 1) + (k & 1);
+                        oR[o] = Rc[k]; oB[o] = Bc[k];
+                    }
+                }
+            }
+        }
+    }
+    PYSP_SYNC();
+
+    // ---------------- phase 3: homogeneity counts for the tile + 1 px ---------------------------------------
+    {
+        constexpr int BW = L::CW / 2, BH = L::CH / 2;
+        PYSP_ITEMS(it, BW * BH) {
+            int by = it / BW, bx = it - by * BW;
+            int cy = 2 * by, cx = 2 * bx;                 // count-region coords of the block's top-left pixel
+            int fy = y0 - 1 + cy, fx = x0 - 1 + cx;       // frame coords
+            // Lab-region local coords of the 4x4 window (edge-duplicated at the frame border, ahd.py:64)
+            int wy[4], wx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wy[k] = EDGE ? clampi(fy - 1 + k, H) - (y0 - 2) : cy + k;
+                wx[k] = EDGE ? clampi(fx - 1 + k, W) - (x0 - 2) : cx + k;
+            }
+            uint32_t res[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                const float* iL = labL + dir * (L::LH * L::LW);
+                const uint32_t* iAB = labAB + dir * (L::LH * L::LW);
+                float wl[4][4], wa[4][4], wb[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int o = wy[a] * L::LW + wx[b];
+                        wl[a][b] = iL[o];
+                        uint32_t ab = iAB[o];
+                        wa[a][b] = ab_lo(ab); wb[a][b] = ab_hi(ab);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int a = 1 + (k >> 1), b = 1 + (k & 1);
+                    const int a1 = dir ? a - 1 : a, b1 = dir ? b : b - 1;     // neighbours along the direction
+                    const int a2 = dir ? a + 1 : a, b2 = dir ? b : b + 1;
+                    float l0 = wl[a][b], a0 = wa[a][b], b0 = wb[a][b];
+                    float epsl = fmaxf(fabsf(l0 - wl[a1][b1]), fabsf(l0 - wl[a2][b2]));
+                    float da1 = a0 - wa[a1][b1], db1 = b0 - wb[a1][b1];
+                    float da2 = a0 - wa[a2][b2], db2 = b0 - wb[a2][b2];
+                    float epsc = fmaxf((da1 * da1) + (db1 * db1), (da2 * da2) + (db2 * db2));
+                    int n = 0;
+#pragma unroll
+                    for (int u = -1; u <= 1; ++u)
+#pragma unroll
+                        for (int v = -1; v <= 1; ++v) {
+                            float dl = wl[a + u][b + v] - l0;                  // signed (pyx:56)
+                            float da = wa[a + u][b + v] - a0, db = wb[a + u][b + v] - b0;
+                            float d2 = (da * da) + (db * db);
+                            n += (dl <= epsl && d2 <= epsc) ? 1 : 0;
+                        }
+                    res[k] |= (uint32_t)n << (4 * dir);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cnt[(cy + (k >> 1)) * L::CW + cx + (k & 1)] = (uint8_t)res[k];
+        }
+    }
+    PYSP_SYNC();
+
+    // ---------------- phase 4: 3x3 vote, select, epilogue, store ----------------------------------------------
+    {
+        constexpr int OW = TW / 2, OH = TH / 2;
+        PYSP_ITEMS(it, OW * OH) {
+            int oy = it / OW, ox = it - oy * OW;
+            int ty = 2 * oy, tx = 2 * ox;                 // tile coords of the quad
+            int fy = y0 + ty, fx = x0 + tx;
+            if (fy >= p.y_end || fx >= W) continue;       // partial tile (even dims: whole quad in or out)
+            int wy[4], wx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wy[k] = EDGE ? reflect101(fy - 1 + k, H) - (y0 - 1) : ty + k;      // cv2.blur: REFLECT_101
+                wx[k] = EDGE ? reflect101(fx - 1 + k, W) - (x0 - 1) : tx + k;
+            }
+            int sh[4][4], sv[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    int c = cnt[wy[a] * L::CW + wx[b]];
+                    sh[a][b] = c & 15; sv[a][b] = c >> 4;
+                }
+            int qi = (oy + 3) * QW + ox + 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int a = k >> 1, b = k & 1;
+                int sumh = 0, sumv = 0;
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) { sumh += sh[a + u][b + v]; sumv += sv[a + u][b + v]; }
+                const bool pick_h = sumh < sumv;          // ties -> V (ahd.py:139)
+                int o = (ty + a) * TW + tx + b;
+                Rgb v;
+                v.r = pick_h ? cand[0 * TH * TW + o] : cand[2 * TH * TW + o];
+                v.b = pick_h ? cand[1 * TH * TW + o] : cand[3 * TH * TW + o];
+                if (k == 0) v.g = pick_h ? Q[L::P_GHR * QN + qi] : Q[L::P_GVR * QN + qi];
+                else if (k == 1) v.g = Q[L::P_G1 * QN + qi];
+                else if (k == 2) v.g = Q[L::P_G2 * QN + qi];
+                else v.g = pick_h ? Q[L::P_GHB * QN + qi] : Q[L::P_GVB * QN + qi];
+                v = finish_pixel(p.c, p.out_kind, v);
+                int yy = fy + a, xx = fx + b;
+                if (p.store_flip) {                       // stored orientation (image.py:181)
+                    if (p.g.flip_y) yy = H - 1 - yy;
+                    if (p.g.flip_x) xx = W - 1 - xx;
+                }
+                char* row = (char*)p.out + (long long)(yy - p.out_row0) * p.out_pitch;
+                if (p.out_kind == OUT_LIN_F16) {
+#ifndef PYSP_HOST_EMU
+                    __half* o16 = (__half*)row + 3 * (long long)xx;
+                    o16[0] = __float2half_rn(v.r); o16[1] = __float2half_rn(v.g); o16[2] = __float2half_rn(v.b);
+#endif
+                } else {
+                    float* o32 = (float*)row + 3 * (long long)xx;
+                    o32[0] = v.r; o32[1] = v.g; o32[2] = v.b;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace pysp

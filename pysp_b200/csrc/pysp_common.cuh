@@ -1,0 +1,203 @@
+// pysp_b200 -- shared definitions for the develop-path kernels (sm_100a).
+//
+// All arithmetic on the path is specified operation by operation (oracle/ahd_spec.py, SURVEY.md
+// Appendix B): every float32 op is rounded individually.  The device build therefore uses
+// `-fmad=false` (no implicit FMA contraction); `fmaf()` is written explicitly only where the product
+// is exact (power-of-two weights), so that it equals mul-then-add bit for bit.
+//
+// The tile functions in ahd_select.cuh / median_stage.cuh are written as *phases* separated by
+// block barriers.  Inside a phase every work item is independent, so the same source also compiles
+// for the host (PYSP_HOST_EMU, used only by tests/host_emu to debug tile logic without a GPU) where a
+// phase simply runs its work items serially.  The product library never contains that build.
+#pragma once
+#include <stdint.h>
+
+#ifdef PYSP_HOST_EMU
+#include <math.h>
+#include <string.h>
+#define PYSP_HD inline
+#define PYSP_D inline
+#define PYSP_SYNC() ((void)0)
+#define PYSP_ITEMS(var, n) for (int var = 0; var < (n); ++var)
+static inline float pysp_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t pysp_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+template <typename T> static inline T pysp_ldg(const T* p) { return *p; }
+#else
+#include <cuda_runtime.h>
+#define PYSP_HD __device__ __forceinline__
+#define PYSP_D __device__ __forceinline__
+#define PYSP_SYNC() __syncthreads()
+#define PYSP_ITEMS(var, n) for (int var = threadIdx.x; var < (n); var += blockDim.x)
+__device__ __forceinline__ float pysp_as_float(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t pysp_as_uint(float f) { return __float_as_uint(f); }
+template <typename T> __device__ __forceinline__ T pysp_ldg(const T* p) { return __ldg(p); }
+#endif
+
+namespace pysp {
+
+// ---- constants of the reference algorithm ---------------------------------------------------------
+// debayer/ahd.py:89-94: h = normalise(0.125*h_optimal + 0.875*h_fast) evaluated in float32.
+#define PYSP_H0 (-0x1.053316p-2f)
+#define PYSP_H1 (0x1p-1f)
+#define PYSP_H2 (0x1.053316p-1f)
+// cv2.getGaussianKernel(3, 1.0) in float32 (debayer/ahd.py:120-121)
+#define PYSP_GK0 (0.27406862f)
+#define PYSP_GK1 (0.45186275f)
+
+enum InKind { IN_U16 = 0, IN_F32 = 1 };
+enum OutKind { OUT_CAM_F32 = 0, OUT_LIN_F32 = 1, OUT_LIN_F16 = 2 };
+
+struct FrameGeom {
+    int H, W;            // frame size (even); flips keep the size
+    int flip_y, flip_x;  // image.py:143-152: logical RGGB coord (y,x) <-> stored (fy?H-1-y:y, fx?W-1-x:x)
+};
+
+struct ColorParams {
+    float wb[3];         // reciprocal neutral multipliers (wb_cct/cam_wb.py:243)
+    double m_metric[9];  // camera -> linear sRGB used by the homogeneity metric (debayer/ahd.py:45-48)
+    double m_out[9];     // camera -> linear sRGB of to_lin_srgb (base_types/image_base.py:62-64)
+    int hdr;             // debayer/ahd.py:52-59
+    int gamma;           // apply lin_srgb_to_srgb in the epilogue (colorize/transform.py:89-99)
+};
+
+struct SelectParams {    // K1: mosaic -> selected camera RGB (or final output when no median stage)
+    FrameGeom g;
+    ColorParams c;
+    int in_kind;
+    const void* in;      // stored orientation; row `in_row0` is the first row present
+    long long in_pitch;  // bytes
+    int in_row0, in_row1;
+    float black[4], white[4];   // by stored-mosaic position TL,TR,BL,BR (normalization.py:20-23)
+    const uint2* lut;    // 33^3 nodes of {L,a,b,0} int16 (device)
+    int out_kind;
+    void* out;           // [rows][W][3]; row `out_row0` (orientation of the store, see store_flip) is the first row
+    long long out_pitch;
+    int out_row0;
+    int store_flip;      // 1: write in stored orientation (image.py:181), 0: logical orientation (scratch)
+    int y_begin, y_end;  // logical rows to produce (even)
+    int tiles_x;
+};
+
+struct MedianParams {    // K2: one postprocess stage (debayer/ahd.py:148-161) on camera RGB
+    FrameGeom g;
+    ColorParams c;
+    const float* in;     // [rows][W][3] logical orientation, row in_row0 first
+    long long in_pitch;
+    int in_row0, in_row1;
+    int out_kind;
+    void* out;
+    long long out_pitch;
+    int out_row0;
+    int store_flip;
+    int y_begin, y_end;
+    int tiles_x;
+};
+
+// ---- border index maps -----------------------------------------------------------------------------
+PYSP_HD int clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }          // REPLICATE / 1-px BORDER_REFLECT
+PYSP_HD int reflect101(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+// quarter-plane edge duplication expressed on full-res mosaic coordinates (debayer/ahd.py:77-80):
+// keeps the CFA phase.
+PYSP_HD int phase_clamp(int v, int n) { return v < 0 ? (v & 1) : (v >= n ? n - 2 + (v & 1) : v); }
+
+// ---- float64 3x3, canonical order ((m0*c0 + m1*c1) + m2*c2), unfused; result rounded to float32 ------
+PYSP_HD float dot3_f64(const double* m, float c0, float c1, float c2) {
+#ifdef __CUDA_ARCH__
+    double a = __dadd_rn(__dmul_rn(m[0], (double)c0), __dmul_rn(m[1], (double)c1));
+    return __double2float_rn(__dadd_rn(a, __dmul_rn(m[2], (double)c2)));
+#else
+    volatile double p0 = m[0] * (double)c0, p1 = m[1] * (double)c1, p2 = m[2] * (double)c2;
+    volatile double a = p0 + p1;
+    return (float)(a + p2);
+#endif
+}
+
+PYSP_HD float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+// colorize/transform.py:98-99 in float32
+PYSP_HD float srgb_gamma(float v) {
+    float x = clip01(v);
+    return x <= 0.0031308f ? x * 12.92f : (1.055f * powf(x, (float)(1.0 / 2.4))) - 0.055f;
+}
+
+// ---- cv2 RGB->Lab (float32 path) : quantise, trilinear in the 33^3 int16 table -----------------------
+// Returns L as the reference float (v*100/16384) and (a,b) as the raw integers v (a = v/64-128 exactly,
+// so differences and squared distances of the integers are the reference's scaled by exact powers of
+// two; every comparison in the homogeneity count is unchanged).
+struct LabQ { float L; uint32_t ab; };
+
+PYSP_HD int quant14(float v) {
+    // cvRound(clip(v,0,1)*16384): the product is exact, adding 2^23 rounds half-to-even
+    float y = clip01(v) * 16384.0f + 8388608.0f;
+    return (int)(pysp_as_uint(y) & 0x7FFFFFu);
+}
+
+PYSP_HD LabQ lab_lookup(const uint2* __restrict__ lut, float r, float g, float b) {
+    int cr = quant14(r), cg = quant14(g), cb = quant14(b);
+    int tr = cr >> 9, tg = cg >> 9, tb = cb >> 9;
+    int sr = (cr >> 5) & 15, sg = (cg >> 5) & 15, sb = (cb >> 5) & 15;
+    // upper corner index is clamped: it only matters when its weight is zero (c == 16384)
+    int tr1 = tr < 32 ? tr + 1 : 32, tg1 = tg < 32 ? tg + 1 : 32, tb1 = tb < 32 ? tb + 1 : 32;
+    int accL = 2048, accA = 2048, accB = 2048;
+#define PYSP_CORNER(ir, ig, ib, w)                                                 \
+    {                                                                              \
+        uint2 e = pysp_ldg(lut + ((ir) * 33 + (ig)) * 33 + (ib));                  \
+        int wv = (w);                                                              \
+        accL += (int)(e.x & 0xFFFFu) * wv;                                         \
+        accA += (int)(e.x >> 16) * wv;                                             \
+        accB += (int)(e.y & 0xFFFFu) * wv;                                         \
+    }
+    int wr0 = 16 - sr, wg0 = 16 - sg, wb0 = 16 - sb;
+    int w00 = wr0 * wg0, w01 = wr0 * sg, w10 = sr * wg0, w11 = sr * sg;
+    PYSP_CORNER(tr, tg, tb, w00 * wb0)
+    PYSP_CORNER(tr, tg, tb1, w00 * sb)
+    PYSP_CORNER(tr, tg1, tb, w01 * wb0)
+    PYSP_CORNER(tr, tg1, tb1, w01 * sb)
+    PYSP_CORNER(tr1, tg, tb, w10 * wb0)
+    PYSP_CORNER(tr1, tg, tb1, w10 * sb)
+    PYSP_CORNER(tr1, tg1, tb, w11 * wb0)
+    PYSP_CORNER(tr1, tg1, tb1, w11 * sb)
+#undef PYSP_CORNER
+    LabQ q;
+    int vL = accL >> 12, vA = accA >> 12, vB = accB >> 12;     // table values are non-negative
+    q.L = (pysp_as_float(0x4B000000u | (uint32_t)vL) - 8388608.0f) * (100.0f / 16384.0f);
+    q.ab = (uint32_t)vA | ((uint32_t)vB << 16);
+    return q;
+}
+
+// integer-valued float from a 16-bit field, offset by 2^23 (differences of two such values are exact)
+PYSP_HD float ab_lo(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab & 0xFFFFu)); }
+PYSP_HD float ab_hi(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab >> 16)); }
+
+// debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
+PYSP_HD LabQ metric_lab(const ColorParams& c, const uint2* __restrict__ lut, float r, float g, float b) {
+    float c0 = r * c.wb[0], c1 = g * c.wb[1], c2 = b * c.wb[2];        // WB applied a 2nd time (ahd.py:46-48)
+    float sr = dot3_f64(c.m_metric + 0, c0, c1, c2);
+    float sg = dot3_f64(c.m_metric + 3, c0, c1, c2);
+    float sb = dot3_f64(c.m_metric + 6, c0, c1, c2);
+    if (c.hdr) {
+        float luma = ((0.2126f * sr) + (0.7152f * sg)) + (0.0722f * sb);
+        LabQ q = lab_lookup(lut, sr / (1.0f + sr), sg / (1.0f + sg), sb / (1.0f + sb));
+        q.L = luma;
+        return q;
+    }
+    return lab_lookup(lut, sr, sg, sb);
+}
+
+// ---- output epilogue ------------------------------------------------------------------------------------
+// camera RGB -> stored pixel.  OUT_CAM_F32: as is.  OUT_LIN_*: clip to [0,1], float64 3x3
+// (colorize/transform.py:37-53), optional gamma.
+struct Rgb { float r, g, b; };
+
+PYSP_HD Rgb finish_pixel(const ColorParams& c, int out_kind, Rgb v) {
+    if (out_kind == OUT_CAM_F32) return v;
+    float c0 = clip01(v.r), c1 = clip01(v.g), c2 = clip01(v.b);
+    Rgb o;
+    o.r = dot3_f64(c.m_out + 0, c0, c1, c2);
+    o.g = dot3_f64(c.m_out + 3, c0, c1, c2);
+    o.b = dot3_f64(c.m_out + 6, c0, c1, c2);
+    if (c.gamma) { o.r = srgb_gamma(o.r); o.g = srgb_gamma(o.g); o.b = srgb_gamma(o.b); }
+    return o;
+}
+
+}  // namespace pysp

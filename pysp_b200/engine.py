@@ -1,0 +1,201 @@
+"""Device plumbing between the Python drop-in layer and the C ABI (libpysp_b200.so).
+
+PyTorch is used only for device memory, streams and (elsewhere) torch.distributed; every computation on
+the develop path happens in the CUDA kernels behind the C ABI.  There is no CPU path: calling into this
+module without a CUDA device raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import torch
+
+from . import _capi
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lab_lut33_i16.npy")
+_lock = threading.Lock()
+_lut_dev = {}       # device index -> packed Lab table (uint8 tensor)
+_scratch = {}       # (device index, stream handle) -> uint8 tensor, grow-only
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pysp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def lab_lut(device):
+    """Device copy of the cv2 RGB->Lab interpolation table (see tools/harvest_lab_lut.py)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    with _lock:
+        t = _lut_dev.get(idx)
+        if t is None:
+            lut = np.ascontiguousarray(np.load(_DATA).astype(np.int16))
+            packed = np.empty(int(_capi.lib().pysp_lab_lut_bytes()), dtype=np.uint8)
+            _capi.check(_capi.lib().pysp_lab_lut_pack_host(lut.ctypes.data, packed.ctypes.data))
+            t = torch.from_numpy(packed).to("cuda:%d" % idx)
+            _lut_dev[idx] = t
+    return t
+
+
+def _get_scratch(device, nbytes, stream):
+    if nbytes <= 0:
+        return None
+    key = (torch.device(device).index, _stream_ptr(stream))
+    with _lock:
+        t = _scratch.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            _scratch[key] = t
+    return t
+
+
+def release_scratch():
+    with _lock:
+        _scratch.clear()
+
+
+def to_device(a, device=None, dtype=None):
+    """NumPy / CPU tensor / CUDA tensor -> contiguous CUDA tensor (no copy if already there)."""
+    require_cuda()
+    if isinstance(a, np.ndarray):
+        if a.dtype == np.uint16:
+            a = a.view(np.int16)                     # same bits; uint16 tensors have no CPU kernels
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = a
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_cuda:
+        t = t.to(device if device is not None else "cuda", non_blocking=True)
+    return t.contiguous()
+
+
+_OUT_KINDS = {"cam": _capi.OUT_CAM_F32, "lin": _capi.OUT_LIN_F32, "lin_f16": _capi.OUT_LIN_F16}
+
+
+def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white=None, hdr=False, gamma=False,
+            out="lin", out_tensor=None, rows=None, frame_height=None, in_row0=0, out_row0=None, stream=None):
+    """Run the fused develop chain on one frame (or one row band of it) that is resident on the GPU.
+
+    mosaic      CUDA tensor [rows_held, W]: uint16/int16 sensor counts (normalisation fused, needs
+                black/white in the reference order [TL,TR,BR,BL]) or float32 `sensor_scaled`.
+    rows        (row_begin, row_end) of the stored frame to produce; default the whole frame.
+    frame_height / in_row0   when `mosaic` holds only rows [in_row0, in_row0+rows_held) of a taller frame.
+    Returns a CUDA tensor [row_end-row_begin, W, 3] (float32, or float16 for out="lin_f16").
+    """
+    require_cuda()
+    L = _capi.lib()
+    if not mosaic.is_cuda:
+        raise ValueError("engine.develop: mosaic must be a CUDA tensor (use engine.to_device)")
+    if mosaic.dim() != 2:
+        raise ValueError("engine.develop: mosaic must be 2-D")
+    if mosaic.stride(1) != 1:
+        mosaic = mosaic.contiguous()
+    held, W = mosaic.shape
+    H = int(frame_height) if frame_height is not None else held
+    if mosaic.dtype in (torch.uint16, torch.int16):
+        in_kind = _capi.IN_U16
+        if black is None or white is None:
+            raise ValueError("engine.develop: black/white levels are required for integer mosaics")
+    elif mosaic.dtype == torch.float32:
+        in_kind = _capi.IN_F32
+    else:
+        raise ValueError("engine.develop: unsupported mosaic dtype %s" % mosaic.dtype)
+    rb, re = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+    kind = _OUT_KINDS[out]
+    odt = torch.float16 if kind == _capi.OUT_LIN_F16 else torch.float32
+    if out_row0 is None:
+        out_row0 = rb
+    dev = mosaic.device
+    with torch.cuda.device(dev):
+        if out_tensor is None:
+            out_tensor = torch.empty((re - out_row0, W, 3), dtype=odt, device=dev)
+        elif (not out_tensor.is_cuda or out_tensor.dtype != odt or out_tensor.dim() != 3
+              or out_tensor.shape[1] != W or out_tensor.shape[2] != 3 or out_tensor.stride(2) != 1
+              or out_tensor.stride(1) != 3 or out_tensor.shape[0] < re - out_row0):
+            raise ValueError("engine.develop: out_tensor has the wrong shape/dtype/layout")
+        nscr = int(L.pysp_develop_scratch_bytes(W, re - rb, int(stages)))
+        scratch = _get_scratch(dev, nscr, stream)
+        lut = lab_lut(dev)
+        a = _capi.fill_develop_args(
+            H, W, pattern, in_kind, mosaic.data_ptr(), mosaic.stride(0) * mosaic.element_size(), in_row0, held,
+            black, white, wb, cam_to_srgb, stages, hdr, gamma, kind, out_tensor.data_ptr(),
+            out_tensor.stride(0) * out_tensor.element_size(), out_row0, rb, re,
+            scratch.data_ptr() if scratch is not None else None, nscr, lut.data_ptr())
+        _capi.check(L.pysp_develop(C.byref(a), _stream_ptr(stream)))
+    return out_tensor
+
+
+def normalize(raw, black, white, stream=None):
+    """bayer_normalize on the device: uint16 [H,W] -> float32 [H,W]."""
+    require_cuda()
+    L = _capi.lib()
+    H, W = raw.shape
+    out = torch.empty((H, W), dtype=torch.float32, device=raw.device)
+    b = (C.c_float * 4)(*[float(v) for v in black[:4]])
+    w = (C.c_float * 4)(*[float(v) for v in white[:4]])
+    with torch.cuda.device(raw.device):
+        _capi.check(L.pysp_normalize_u16(raw.data_ptr(), raw.stride(0) * 2, out.data_ptr(), out.stride(0) * 4, H, W,
+                                         b, w, _stream_ptr(stream)))
+    return out
+
+
+def cam_to_rgb(rgb, matrix, clip=True, gamma=False, half=False, stream=None):
+    """float32 [...,3] camera RGB -> float64 3x3 -> float32 (colorize/transform.py:37-53)."""
+    require_cuda()
+    L = _capi.lib()
+    rgb = rgb.contiguous()
+    out = torch.empty(rgb.shape, dtype=torch.float16 if half else torch.float32, device=rgb.device)
+    m = (C.c_double * 9)(*[float(v) for row in np.asarray(matrix, dtype=np.float64) for v in row])
+    with torch.cuda.device(rgb.device):
+        _capi.check(L.pysp_cam_to_lin_srgb(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, m, int(bool(clip)),
+                                           int(bool(gamma)), int(bool(half)), _stream_ptr(stream)))
+    return out
+
+
+def srgb_gamma(rgb, stream=None):
+    require_cuda()
+    L = _capi.lib()
+    rgb = rgb.contiguous()
+    out = torch.empty_like(rgb)
+    with torch.cuda.device(rgb.device):
+        _capi.check(L.pysp_lin_srgb_to_srgb(rgb.data_ptr(), out.data_ptr(), rgb.numel(), _stream_ptr(stream)))
+    return out
+
+
+def fuse_exposures(brackets, ev_offsets, bias, brightest, want_count=True, stream=None):
+    """raw_hdr.py:135-148 on the device.  brackets: list of float32 CUDA tensors [H,W] with equal strides."""
+    require_cuda()
+    L = _capi.lib()
+    n = len(brackets)
+    H, W = brackets[0].shape
+    dev = brackets[0].device
+    brackets = [b if b.stride(1) == 1 else b.contiguous() for b in brackets]
+    pitch = brackets[0].stride(0) * 4
+    for b in brackets:
+        if b.shape != (H, W) or b.dtype != torch.float32 or b.device != dev:
+            raise ValueError("fuse_exposures: brackets must be float32 [H,W] on one device")
+        if b.stride(0) * 4 != pitch:
+            raise ValueError("fuse_exposures: brackets must share one row pitch")
+    out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    cnt = torch.empty((H, W), dtype=torch.int32, device=dev) if want_count else None
+    ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in brackets])
+    evo = (C.c_float * n)(*[float(v) for v in ev_offsets])
+    bia = (C.c_float * (3 * n))(*[float(v) for v in np.asarray(bias, dtype=np.float32).reshape(-1)])
+    with torch.cuda.device(dev):
+        _capi.check(L.pysp_fuse_exposures(ptrs, n, pitch, H, W, evo, bia, int(brightest), out.data_ptr(),
+                                          out.stride(0) * 4, cnt.data_ptr() if cnt is not None else None,
+                                          (cnt.stride(0) * 4) if cnt is not None else 0, _stream_ptr(stream)))
+    return out, cnt
+
+
+def kernel_launches():
+    return int(_capi.lib().pysp_kernel_launches())

@@ -1,0 +1,117 @@
+"""Multi-GPU partitioning of the develop path: one process per GPU, torch.distributed for plumbing.
+
+The reference has no distributed code; the path shards naturally:
+  * batches of frames / HDR sets  -> whole frames round-robin over ranks, NO data-path collective;
+  * one very large frame          -> contiguous, even-aligned row bands; each rank needs 6 + 4*stages
+                                     mosaic rows of its neighbours: one halo exchange of RAW rows between
+                                     adjacent ranks (NCCL send/recv = NVLink P2P), recompute in the halo,
+                                     never exchange intermediates; the result is bit-identical to 1 GPU;
+  * HDR brackets spread over ranks -> one exchange step (every rank pulls its band's rows of every
+                                     bracket from the owners) so that each rank accumulates the brackets
+                                     in list order, like raw_hdr.py:135-139, bit for bit.
+The exchange helpers work on CUDA tensors with the NCCL backend and on CPU tensors with gloo (tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def frames_for_rank(n_frames, rank, world):
+    """Whole-frame sharding: frame i goes to rank i % world."""
+    return list(range(rank, n_frames, world))
+
+
+def band_rows(height, world, rank):
+    """Even-aligned contiguous row band [begin, end) of `rank`; bands tile [0, height)."""
+    quads = height // 2
+    base, extra = divmod(quads, world)
+    begin = rank * base + min(rank, extra)
+    end = begin + base + (1 if rank < extra else 0)
+    return 2 * begin, 2 * end
+
+
+def halo_rows(stages):
+    return 6 + 4 * max(int(stages), 0)
+
+
+def band_with_halo(height, world, rank, stages):
+    """(band_begin, band_end, held_begin, held_end): rows a rank must hold to develop its band."""
+    b, e = band_rows(height, world, rank)
+    h = halo_rows(stages)
+    return b, e, max(0, b - h), min(height, e + h)
+
+
+def exchange_halo(band, height, stages, group=None):
+    """band: [rows, W] tensor holding exactly this rank's band rows.  Returns ([held_rows, W] tensor,
+    held_begin): the band extended by the neighbours' raw rows.  Bands shorter than the halo pull from
+    ranks further away, so every rank sends each peer exactly the rows that peer needs."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b, e, hb, he = band_with_halo(height, world, rank, stages)
+    assert band.shape[0] == e - b, (band.shape, b, e)
+    held = torch.empty((he - hb,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+    held[b - hb:e - hb].copy_(band)
+    ops, keep = [], []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        pb, pe, phb, phe = band_with_halo(height, world, peer, stages)
+        # rows of mine that the peer needs
+        s0, s1 = max(b, phb), min(e, phe)
+        if s0 < s1:
+            t = band[s0 - b:s1 - b].contiguous()
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend, t, peer, group))
+        # rows of the peer that I need
+        r0, r1 = max(pb, hb), min(pe, he)
+        if r0 < r1:
+            ops.append(dist.P2POp(dist.irecv, held[r0 - hb:r1 - hb], peer, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return held, hb
+
+
+def exchange_brackets_by_rows(my_brackets, n_brackets, height, halo, group=None, like=None):
+    """HDR brackets live on rank (index % world) as whole [H, W] float32 mosaics (`my_brackets` maps
+    bracket index -> tensor).  Returns the list of all n brackets restricted to this rank's rows
+    [held_begin, held_end) = band +- halo, in list order, plus held_begin.  A rank that owns no
+    bracket (world > n) passes `like`, an empty [0, W] tensor of the right dtype/device."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    any_t = next(iter(my_brackets.values())) if my_brackets else like
+    width = any_t.shape[1]
+
+    def held_range(r):
+        b, e = band_rows(height, world, r)
+        return max(0, b - halo), min(height, e + halo)
+
+    hb, he = held_range(rank)
+    out = [None] * n_brackets
+    ops, keep = [], []
+    for k in range(n_brackets):
+        owner = k % world
+        if owner == rank:
+            out[k] = my_brackets[k][hb:he].contiguous()
+            for peer in range(world):
+                if peer != rank:
+                    pb, pe = held_range(peer)
+                    t = my_brackets[k][pb:pe].contiguous()
+                    keep.append(t)
+                    ops.append(dist.P2POp(dist.isend, t, peer, group))
+        else:
+            out[k] = torch.empty((he - hb, width), dtype=any_t.dtype, device=any_t.device)
+            ops.append(dist.P2POp(dist.irecv, out[k], owner, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out, hb
+
+
+def develop_band(band_mosaic, height, stages, develop_fn, group=None):
+    """Single large frame over row bands: exchange raw halo rows, then develop this rank's band.
+    develop_fn(held, in_row0, rows) -> the band's output (engine.develop on the GPU)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    held, hb = exchange_halo(band_mosaic, height, stages, group)
+    b, e = band_rows(height, world, rank)
+    return develop_fn(held, hb, (b, e))

@@ -1,0 +1,195 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures of the reference and against
+the oracle on seeded inputs.  Bit-exact for everything up to linear sRGB; the sRGB gamma (powf) to 1e-4
+relative, the tolerance BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_bit_equal, golden, golden_develop_cases
+from oracle import ahd_spec as sp
+from pysp_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+WB = syn.wb_multipliers()
+M = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pysp_b200 import engine, _capi
+    assert torch.cuda.is_available(), "these tests need the GPU"
+    _capi.lib()                       # fails loudly if the CUDA extension is missing
+    return engine
+
+
+def gpu_develop(eng, src, stages, pattern="RGGB", black=syn.BLACK, white=syn.WHITE, out="lin", hdr=False, **kw):
+    t = eng.to_device(src)
+    r = eng.develop(t, WB, M, stages=stages, pattern=pattern, black=black, white=white, hdr=hdr, out=out, **kw)
+    torch.cuda.synchronize()
+    return r.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_develop_cases())
+def test_golden_fixtures(eng, name):
+    d = golden(name)
+    args = (d["raw"], int(d["stages"]), str(d["pattern"]), d["black"], d["white"])
+    assert_bit_equal(gpu_develop(eng, *args, out="cam"), d["cam"], "camera RGB")
+    assert_bit_equal(gpu_develop(eng, *args, out="lin"), d["lin"], "linear sRGB")
+
+
+@pytest.mark.parametrize("stages", [0, 1])
+def test_golden_hdr(eng, stages):
+    d = golden("hdr48x64_s%d" % stages)
+    assert_bit_equal(gpu_develop(eng, d["sensor"], stages, hdr=True, out="cam"), d["cam"], "HDR camera RGB")
+    assert_bit_equal(gpu_develop(eng, d["sensor"], stages, hdr=True, out="lin"), d["lin"], "HDR linear sRGB")
+
+
+@pytest.mark.parametrize("shape,stages,seed", [((512, 768), 1, 0), ((250, 1002), 0, 1), ((1000, 1500), 3, 2),
+                                               ((130, 62), 2, 3)])
+def test_against_oracle(eng, shape, stages, seed):
+    raw = syn.scene(shape[0], shape[1], seed)
+    lin, cam, ex = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages, keep=True)
+    got0 = gpu_develop(eng, raw, 0, out="cam")
+    # AHD direction choice: the selected image equals the oracle's selection everywhere
+    assert_bit_equal(got0, ex["selected"], "selected camera RGB (direction map)")
+    assert_bit_equal(gpu_develop(eng, raw, stages, out="cam"), cam, "camera RGB")
+    assert_bit_equal(gpu_develop(eng, raw, stages, out="lin"), lin, "linear sRGB")
+
+
+@pytest.mark.parametrize("pattern", ["BGGR", "GRBG", "GBRG"])
+def test_patterns(eng, pattern):
+    raw = syn.scene(300, 420, 4)
+    lin, _ = sp.develop(raw, (500, 510, 520, 530), (16383, 16000, 15800, 16100), WB, syn.MAT_XYZ_TO_CAM,
+                        syn.WHITE_XYZ, 1, pattern)
+    assert_bit_equal(gpu_develop(eng, raw, 1, pattern, (500, 510, 520, 530), (16383, 16000, 15800, 16100)), lin, pattern)
+
+
+def test_random_noise_frame(eng):
+    raw = syn.random_mosaic(256, 384, 5)      # white noise: every direction vote is contested
+    lin, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 1)
+    assert_bit_equal(gpu_develop(eng, raw, 1), lin, "white-noise frame")
+
+
+def test_row_bands_equal_whole_frame(eng):
+    raw = syn.scene(600, 400, 6)
+    for stages in (0, 1, 2):
+        whole = gpu_develop(eng, raw, stages)
+        halo = 6 + 4 * stages
+        parts = []
+        for rb, re in ((0, 150), (150, 298), (298, 600)):
+            r0, r1 = max(0, rb - halo), min(600, re + halo)
+            t = eng.to_device(raw[r0:r1])
+            o = eng.develop(t, WB, M, stages=stages, black=syn.BLACK, white=syn.WHITE, rows=(rb, re),
+                            frame_height=600, in_row0=r0)
+            parts.append(o.cpu().numpy())
+        assert_bit_equal(np.concatenate(parts), whole, "bands, stages=%d" % stages)
+
+
+def test_full_size_windows_against_oracle(eng):
+    """24 MP frame (BASELINE config 2): the GPU result inside sampled windows equals the oracle run on the
+    window plus margin (size-independent pin of the full-size run), and repeated runs are identical."""
+    H, W, stages, margin = 4000, 6000, 1, 16
+    raw = syn.scene(H, W, 0)
+    t = eng.to_device(raw)
+    a = eng.develop(t, WB, M, stages=stages, black=syn.BLACK, white=syn.WHITE)
+    b = eng.develop(t, WB, M, stages=stages, black=syn.BLACK, white=syn.WHITE)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    for (y, x) in [(0, 0), (H - 256, W - 256), (1990, 2990), (300, 5744), (3744, 0), (1000, 700)]:
+        y0, y1, x0, x1 = max(0, y - margin), min(H, y + 256 + margin), max(0, x - margin), min(W, x + 256 + margin)
+        lin, _ = sp.develop(raw[y0:y1, x0:x1], syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages)
+        # compare away from the crop's artificial borders, keep the true frame borders
+        cy0 = 0 if y0 == 0 else margin
+        cx0 = 0 if x0 == 0 else margin
+        cy1 = (y1 - y0) if y1 == H else (y1 - y0 - margin)
+        cx1 = (x1 - x0) if x1 == W else (x1 - x0 - margin)
+        got = a[y0 + cy0:y0 + cy1, x0 + cx0:x0 + cx1].cpu().numpy()
+        assert_bit_equal(got, lin[cy0:cy1, cx0:cx1], "window at (%d,%d)" % (y, x))
+
+
+def test_fused_outputs(eng):
+    raw = syn.scene(200, 300, 8)
+    lin, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 1)
+    half = gpu_develop(eng, raw, 1, out="lin_f16")
+    assert half.dtype == np.float16 and np.array_equal(half, lin.astype(np.float16))
+    srgb = gpu_develop(eng, raw, 1, gamma=True)
+    ref = sp.lin_srgb_to_srgb(lin)
+    assert np.all(np.abs(srgb - ref) <= 1e-4 * np.maximum(np.abs(ref), 1e-3))
+
+
+def test_pointwise_entry_points(eng):
+    from pysp_b200 import bayer_normalize, cam_to_lin_srgb, lin_srgb_to_srgb, clip_rgb
+    from pysp_b200.wb_cct import CameraWhiteBalance
+    d = golden("scene64x96_RGGB")
+    assert_bit_equal(bayer_normalize(d["raw"], list(d["black"]), list(d["white"])), d["sensor"], "bayer_normalize")
+    wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    assert_bit_equal(cam_to_lin_srgb(d["cam"], wb.get_matrix()), d["lin"], "cam_to_lin_srgb")
+    x = np.random.default_rng(0).uniform(-0.5, 1.5, size=(33, 17, 3)).astype(np.float32)
+    assert_bit_equal(cam_to_lin_srgb(x, wb.get_matrix(), clip_highlights=False), sp.mat3_f64(x, M), "unclipped matrix")
+    assert_bit_equal(clip_rgb(x), np.clip(x, 0, 1), "clip_rgb")
+    g = golden("gamma")
+    y = lin_srgb_to_srgb(g["x"])
+    assert np.all(np.abs(y - g["y"]) <= 1e-4 * np.maximum(np.abs(g["y"]), 1e-3))
+    t = lin_srgb_to_srgb(torch.from_numpy(g["x"]).cuda())
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), y)
+
+
+def test_drop_in_containers(eng):
+    """RawRgbgDataFromRaw(...).debayer(QualityDemosaic.Best).to_lin_srgb() and lin_srgb_to_srgb."""
+    import pysp_b200 as P
+    from pysp_b200.wb_cct import CameraWhiteBalance
+    d = golden("scene64x96_GRBG")
+    wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    img = P.RawRgbgDataFromRaw.from_mosaic(d["raw"], list(d["black"]), list(d["white"]), P.BayerPattern.Grbg, wb, ev=10.0)
+    dem = img.debayer(P.QualityDemosaic.Best)
+    assert isinstance(dem.image, np.ndarray) and dem.current_ev == 10.0 and dem.is_valid()
+    assert_bit_equal(dem.image, d["cam"], "RawDemosaicData.image")
+    assert_bit_equal(dem.to_lin_srgb(), d["lin"], "to_lin_srgb")
+    assert_bit_equal(img.develop(1), d["lin"], "fused develop")
+    # container path on a float32 sensor (bayer_normalize first), RGGB after to_rggb()
+    img2 = P.RawBayerData()
+    img2.sensor_scaled = P.bayer_normalize(d["raw"], list(d["black"]), list(d["white"]))
+    img2.sensor_pattern = P.BayerPattern.Grbg
+    img2.cam_wb = wb
+    img2.current_ev = 10.0
+    rggb = img2.to_rggb()
+    dem2 = rggb.demosaic(P.QualityDemosaic.Best, postprocess_steps=1)
+    assert_bit_equal(dem2.image, d["cam"], "RawRggbBayerData.demosaic")
+    dem2.wb_undo()
+    dem2.wb_apply()
+    assert np.allclose(dem2.image, d["cam"], rtol=1e-6, atol=1e-7)
+    # CUDA tensors in -> CUDA tensors out
+    img3 = P.RawRgbgDataFromRaw.from_mosaic(torch.from_numpy(d["raw"].view(np.int16)).cuda(), list(d["black"]),
+                                            list(d["white"]), "Grbg", wb, ev=10.0)
+    out = img3.develop(1)
+    assert out.is_cuda
+    assert_bit_equal(out.cpu().numpy(), d["lin"], "device-resident develop")
+
+
+def test_hdr_fuse(eng):
+    import pysp_b200 as P
+    from pysp_b200.wb_cct import CameraWhiteBalance
+    d = golden("fuse5_40x56")
+    wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    imgs = [P.RawRggbBayerData(b, wb, float(e), 1.0) for b, e in zip(d["brackets"], d["evs"])]
+    hdr, cnt = P.fuse_exposures_to_raw(imgs)
+    assert hdr.get_hdr() and hdr.lim_sat == float(d["lim_sat"]) and hdr.current_ev == float(d["target_ev"])
+    assert_bit_equal(hdr.sensor_scaled, d["fused"], "fused mosaic")
+    assert np.array_equal(cnt, d["count"])
+    dem = hdr.demosaic(P.QualityDemosaic.Best, 1)
+    assert_bit_equal(dem.image, d["cam"], "camera RGB of the fused mosaic")
+    assert_bit_equal(dem.to_lin_srgb(), d["lin"], "linear sRGB of the fused mosaic")
+    assert P.fuse_exposures_to_raw([]) is None
+
+
+def test_large_frame_smoke(eng):
+    """100 MP frame (config 5): runs, finite, deterministic checksum across two runs."""
+    H, W = 8660, 11548
+    raw = torch.from_numpy(syn.scene(H // 4, W // 4, 1).view(np.int16)).cuda().repeat(4, 4)[:H, :W].contiguous()
+    a = eng.develop(raw, WB, M, stages=1, black=syn.BLACK, white=syn.WHITE)
+    s1 = a.view(torch.int32).to(torch.int64).sum().item()
+    assert torch.isfinite(a).all()
+    del a
+    b = eng.develop(raw, WB, M, stages=1, black=syn.BLACK, white=syn.WHITE)
+    assert b.view(torch.int32).to(torch.int64).sum().item() == s1

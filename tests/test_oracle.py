@@ -1,0 +1,83 @@
+"""The oracle (oracle/ahd_spec.py) against the golden fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  Bit-exact: every operation on the path is an IEEE basic op or an integer
+table interpolation."""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, golden, golden_develop_cases
+from oracle import ahd_spec as sp
+from pysp_b200 import synthetic as syn
+
+WB = syn.wb_multipliers()
+
+
+@pytest.mark.parametrize("name", golden_develop_cases())
+def test_develop_matches_reference(name):
+    d = golden(name)
+    lin, cam, ex = sp.develop(d["raw"], d["black"], d["white"], WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ,
+                              int(d["stages"]), str(d["pattern"]), keep=True)
+    assert_bit_equal(sp.normalize(d["raw"], d["black"], d["white"]), d["sensor"], "bayer_normalize")
+    assert np.array_equal(ex["cnt_h"], d["cnt_h"]) and np.array_equal(ex["cnt_v"], d["cnt_v"])
+    assert np.array_equal(ex["pick_h"], d["pick_h"])          # AHD direction choice
+    assert_bit_equal(cam, d["cam"], "camera RGB")
+    assert_bit_equal(lin, d["lin"], "linear sRGB")
+
+
+@pytest.mark.parametrize("stages", [0, 1])
+def test_hdr_branch(stages):
+    d = golden("hdr48x64_s%d" % stages)
+    m = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    cam, ex = sp.ahd_demosaic(d["sensor"], WB, m, stages, hdr=True, keep=True)
+    assert np.array_equal(ex["pick_h"], d["pick_h"])
+    assert_bit_equal(cam, d["cam"], "camera RGB (HDR)")
+    assert_bit_equal(sp.to_lin_srgb(cam, m), d["lin"], "linear sRGB (HDR)")
+
+
+def test_fuse_exposures():
+    d = golden("fuse5_40x56")
+    fused, cnt, lim, tev = sp.fuse_exposures(list(d["brackets"]), list(d["evs"]), WB)
+    assert_bit_equal(fused, d["fused"], "fused mosaic")
+    assert np.array_equal(cnt, d["count"])
+    assert lim == float(d["lim_sat"]) and tev == float(d["target_ev"])
+    m = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    cam = sp.ahd_demosaic(fused, WB, m, 1, hdr=True)
+    assert_bit_equal(cam, d["cam"], "camera RGB of the fused mosaic")
+    assert_bit_equal(sp.to_lin_srgb(cam, m), d["lin"], "linear sRGB of the fused mosaic")
+
+
+def test_gamma():
+    d = golden("gamma")
+    assert_bit_equal(sp.lin_srgb_to_srgb(d["x"]), d["y"], "lin_srgb_to_srgb")
+
+
+def test_constants():
+    d = golden("kernels")
+    assert np.array_equal(np.stack(sp.phase_kernels(False)), d["base_tl"])
+    assert np.array_equal(np.stack(sp.phase_kernels(True)), d["base_br"])
+    g = d["gauss3"].ravel()
+    assert g[0] == sp.GAUSS_K0 and g[1] == sp.GAUSS_K1 and g[2] == sp.GAUSS_K0
+    assert [float(v).hex() for v in sp.H5] == ["-0x1.0533160000000p-2", "0x1.0000000000000p-1",
+                                               "0x1.0533160000000p-1", "0x1.0000000000000p-1",
+                                               "-0x1.0533160000000p-2"]
+
+
+def test_lab_table_against_cv2():
+    """The harvested 33^3 table + integer trilinear restatement reproduces cv2.cvtColor bit for bit
+    (incl. out-of-range inputs and the 1/512 quantisation boundaries)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-0.2, 1.2, size=(1, 400000, 3)).astype(np.float32)
+    k = (rng.integers(0, 16385 * 2, size=(1, 100000, 3)).astype(np.float32) / np.float32(32768.0))
+    x = np.concatenate([x, k.astype(np.float32)], axis=1)
+    assert_bit_equal(sp.lab_cv(x), cv2.cvtColor(x, cv2.COLOR_RGB2LAB), "Lab")
+
+
+def test_cv2_backend_is_close():
+    """The timing backend (same library calls as the reference, optimised OpenCV) agrees with the pinned
+    arithmetic up to the reference's own optimised-vs-generic noise."""
+    pytest.importorskip("cv2")
+    raw = syn.scene(96, 128, 3)
+    a, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 0)
+    b, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 0, backend="cv2")
+    close = np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-3)
+    assert close.mean() > 0.995

@@ -1,0 +1,111 @@
+"""Tile logic of the CUDA kernels, run through the host emulation (tests/host_emu) against the oracle:
+tiling, halos, the six border rules, partial tiles, CFA flips, row bands, HDR.  The emulation compiles the
+very same tile functions as the CUDA build (see tests/host_emu/emu.cpp); it is test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bit_equal
+from oracle import ahd_spec as sp
+from pysp_b200 import _capi
+from pysp_b200 import synthetic as syn
+
+EMU_DIR = os.path.join(ROOT, "tests", "host_emu")
+WB = syn.wb_multipliers()
+M = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libpysp_emu.so")
+    srcs = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(ROOT, "pysp_b200", "csrc", f)
+                                                 for f in os.listdir(os.path.join(ROOT, "pysp_b200", "csrc"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        if not os.path.exists("/usr/bin/g++"):
+            pytest.skip("g++ not available")
+        subprocess.check_call([os.path.join(EMU_DIR, "build.sh")])
+    lib = C.CDLL(so)
+    lib.emu_develop.argtypes = [C.POINTER(_capi.DevelopArgs), C.c_int, C.c_int]
+    lib.emu_last_error.restype = C.c_char_p
+    return lib
+
+
+def packed_lut():
+    l = np.load(os.path.join(ROOT, "pysp_b200", "data", "lab_lut33_i16.npy")).reshape(-1, 3).astype(np.uint16).astype(np.uint32)
+    p = np.zeros((l.shape[0], 2), dtype=np.uint32)
+    p[:, 0] = l[:, 0] | (l[:, 1] << 16)
+    p[:, 1] = l[:, 2]
+    return p
+
+
+LUT = packed_lut()
+
+
+def emu_develop(lib, src, stages, pattern="RGGB", tile=(12, 8), black=syn.BLACK, white=syn.WHITE,
+                out_kind=_capi.OUT_LIN_F32, band=None, hdr=False, held=None):
+    """src: uint16 counts or float32 sensor; `held` = (row0, rows) keeps only that slice of the frame."""
+    H, W = src.shape
+    rb, re = band or (0, H)
+    out = np.full((re - rb, W, 3), np.nan, dtype=np.float32)
+    nscr = (2 if stages >= 2 else 1) * ((re - rb) + 8 * max(stages, 0)) * W * 3
+    scratch = np.full(max(nscr, 1), np.nan, dtype=np.float32)
+    r0, nr = held or (0, H)
+    part = np.ascontiguousarray(src[r0:r0 + nr])
+    a = _capi.fill_develop_args(H, W, pattern, _capi.IN_U16 if src.dtype == np.uint16 else _capi.IN_F32,
+                                part.ctypes.data, part.strides[0], r0, nr, black, white, WB, M, stages, hdr, False,
+                                out_kind, out.ctypes.data, out.strides[0], rb, rb, re, scratch.ctypes.data,
+                                scratch.nbytes, LUT.ctypes.data)
+    rc = lib.emu_develop(C.byref(a), tile[0], tile[1])
+    assert rc == 0, lib.emu_last_error()
+    return out
+
+
+@pytest.mark.parametrize("shape", [(4, 6), (8, 8), (10, 14), (34, 50), (40, 130)])
+@pytest.mark.parametrize("stages", [0, 1, 2])
+def test_frames(emu, shape, stages):
+    raw = syn.scene(shape[0], shape[1], 3) if shape[0] > 10 else syn.random_mosaic(shape[0], shape[1], 3)
+    lin, cam = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages)
+    for tile in ((12, 8), (60, 28)):
+        assert_bit_equal(emu_develop(emu, raw, stages, tile=tile), lin, "lin %s" % (tile,))
+        assert_bit_equal(emu_develop(emu, raw, stages, tile=tile, out_kind=_capi.OUT_CAM_F32), cam, "cam %s" % (tile,))
+
+
+@pytest.mark.parametrize("pattern", ["RGGB", "BGGR", "GRBG", "GBRG"])
+def test_patterns_and_levels(emu, pattern):
+    raw = syn.scene(36, 52, 6)
+    black, white = (500, 510, 520, 530), (16383, 16000, 15800, 16100)
+    lin, _ = sp.develop(raw, black, white, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 1, pattern)
+    assert_bit_equal(emu_develop(emu, raw, 1, pattern, black=black, white=white), lin, pattern)
+
+
+@pytest.mark.parametrize("pattern", ["RGGB", "GRBG"])
+@pytest.mark.parametrize("stages", [0, 1, 2])
+def test_row_bands_equal_whole_frame(emu, stages, pattern):
+    """A band developed from only its rows + halo is bit-identical to the same rows of the whole frame."""
+    raw = syn.scene(64, 40, 7)
+    whole = emu_develop(emu, raw, stages, pattern)
+    halo = 6 + 4 * stages
+    for rb, re in ((0, 20), (20, 44), (44, 64)):
+        r0, r1 = max(0, rb - halo), min(64, re + halo)
+        band = emu_develop(emu, raw, stages, pattern, band=(rb, re), held=(r0, r1 - r0))
+        assert_bit_equal(band, whole[rb:re], "band [%d,%d)" % (rb, re))
+
+
+def test_hdr_and_f32_input(emu):
+    rng = np.random.default_rng(9)
+    sensor = (syn.scene(32, 44, 9).astype(np.float32) / 16383.0) * np.where(rng.random((32, 44)) < 0.2, 3.0, 1.0)
+    sensor = sensor.astype(np.float32)
+    for stages in (0, 1):
+        cam = sp.ahd_demosaic(sensor, WB, M, stages, hdr=True)
+        assert_bit_equal(emu_develop(emu, sensor, stages, hdr=True, out_kind=_capi.OUT_CAM_F32), cam, "hdr cam")
+        assert_bit_equal(emu_develop(emu, sensor, stages, hdr=True), sp.to_lin_srgb(cam, M), "hdr lin")
+
+
+def test_golden_through_emulation(emu):
+    from conftest import golden
+    d = golden("scene64x96_BGGR")
+    out = emu_develop(emu, d["raw"], int(d["stages"]), "BGGR", black=d["black"], white=d["white"])
+    assert_bit_equal(out, d["lin"], "golden BGGR")
