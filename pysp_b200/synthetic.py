@@ -18,11 +18,8 @@ def wb_multipliers():
     return (1.0 / neutral()).astype(np.float32)
 
 
-def scene(height, width, seed=0, noise=30.0):
-    """14-bit RGGB mosaic: smooth sinusoids + diagonal high-frequency term, a zone-plate quadrant, a
-    flat quadrant (mass integer ties in the homogeneity vote), a saturated patch (clip path) and
-    Gaussian read noise."""
-    rng = np.random.default_rng(seed)
+def scene_base(height, width):
+    """Noise-free float32 scene in sensor counts (see `scene`)."""
     y, x = np.mgrid[0:height, 0:width].astype(np.float32)
     base = 0.5 + 0.35 * np.sin(x / 37.0) * np.cos(y / 23.0) + 0.1 * np.sin((x + y) / 5.0)
     h2, w2 = height // 2, width // 2
@@ -38,6 +35,16 @@ def scene(height, width, seed=0, noise=30.0):
     img = 15000.0 * base * cast + 512.0
     ph, pw = max(2, height // 8), max(2, width // 8)
     img[ph:2 * ph, pw:2 * pw] = 20000.0                     # saturated patch
+    return img
+
+
+def scene(height, width, seed=0, noise=30.0, base=None):
+    """14-bit RGGB mosaic: smooth sinusoids + diagonal high-frequency term, a zone-plate quadrant, a
+    flat quadrant (mass integer ties in the homogeneity vote), a saturated patch (clip path) and
+    Gaussian read noise.  `base` = scene_base(height, width) may be passed to reuse it across seeds."""
+    rng = np.random.default_rng(seed)
+    img = scene_base(height, width) if base is None else base
+    h2, w2 = height // 2, width // 2
     if noise > 0:
         img = img + rng.normal(0.0, noise, size=img.shape).astype(np.float32)
         img[h2 + h2 // 2:, :w2 // 2] = 15000.0 * 0.42 + 512.0   # part of the flat quadrant is noise-free
