@@ -1,7 +1,9 @@
 // K1: RGGB mosaic tile (+6 px halo) -> AHD direction-selected camera RGB (debayer/ahd.py:69-145).
 //
-// One CTA develops one TW x TH output tile entirely in shared memory:
-//   phase 0  load + normalise (normalization.py:20-25) + white balance (ahd.py:77-80) into four
+// A persistent CTA develops TW x TH output tiles entirely in shared memory.  The raw mosaic box of the
+// NEXT tile is fetched by TMA into a staging buffer while the current tile is computed, and the finished
+// tile leaves through a shared-memory staging tile and a TMA store (see pysp_b200.cu for the pipeline).
+//   phase 0  staging box -> normalise (normalization.py:20-25) + white balance (ahd.py:77-80) into four
 //            quarter-resolution CFA planes (bayer_chan_mixer.py:13-21 becomes index math);
 //   phase 1  5-tap H and V green at R/B sites (ahd.py:97-102) and colour differences;
 //   phase 2  per 2x2 quad and per direction: green high-pass (ahd.py:120-121), 4-phase Gaussian
@@ -9,7 +11,7 @@
 //            cv2-Lab through the 33^3 table (ahd.py:45-62); Lab kept for the tile+2 px, the two
 //            candidate images for the tile only -- neither ever goes to HBM;
 //   phase 3  homogeneity counts (ahd_homogeneity_cython.pyx:36-58) for the tile+1 px;
-//   phase 4  3x3 box vote (ahd.py:133-139), select, epilogue, store.
+//   phase 4  3x3 box vote (ahd.py:133-139), select, epilogue -> output staging tile.
 // All planes are stored phase-separated ("quarter planes") so that a thread that owns a 2x2 quad
 // addresses shared memory with unit stride and compile-time plane offsets.
 //
@@ -18,44 +20,98 @@
 // outside [y_begin,y_end) but inside the frame are read from the buffer like any other halo.
 #pragma once
 #include "pysp_common.cuh"
+#include "tma.cuh"
 
 namespace pysp {
 
 template <int TW_, int TH_>
 struct SelectTile {
     static constexpr int TW = TW_, TH = TH_;
-    static constexpr int QW = (TW + 12) / 2, QH = (TH + 12) / 2;   // quarter planes incl. 3-quad halo
+    static constexpr int BOXW = TW + 12, BOXH = TH + 12;           // raw input box (tile + 6)
+    static constexpr int QW = BOXW / 2, QH = BOXH / 2;             // quarter planes incl. 3-quad halo
     static constexpr int QN = QW * QH;
     static constexpr int LW = TW + 4, LH = TH + 4;                 // Lab region (tile + 2)
     static constexpr int CW = TW + 2, CH = TH + 2;                 // count region (tile + 1)
     // quarter planes (float): mosaic R,G1,G2,B ; H/V green at R and B ; H/V colour difference at R and B
     enum { P_R = 0, P_G1, P_G2, P_B, P_GHR, P_GHB, P_GVR, P_GVB, P_DHR, P_DHB, P_DVR, P_DVB, NPLANES };
-    static constexpr int OFF_Q = 0;                                // floats
-    static constexpr int OFF_LABL = OFF_Q + NPLANES * QN;          // [2][LH][LW] float  L
-    static constexpr int OFF_LABAB = OFF_LABL + 2 * LH * LW;       // [2][LH][LW] u32    a|b<<16
-    static constexpr int OFF_CAND = OFF_LABAB + 2 * LH * LW;       // [4][TH][TW] float  RH,BH,RV,BV
-    static constexpr int OFF_CNT = OFF_CAND + 4 * TH * TW;         // [CH][CW] u8  cntH | cntV<<4
-    static constexpr int SMEM_BYTES = OFF_CNT * 4 + ((CH * CW + 15) / 16) * 16;
-    static_assert(TW % 2 == 0 && TH % 2 == 0, "tile must be quad aligned");
+    static constexpr int align128(int v) { return (v + 127) / 128 * 128; }
+    // byte offsets into dynamic shared memory
+    static constexpr int OFF_BAR = 0;                                            // mbarrier (8 B)
+    static constexpr int OFF_STAGE = 128;                                        // raw box, u16 or f32
+    static constexpr int OFF_Q = align128(OFF_STAGE + BOXW * BOXH * 4);          // NPLANES x [QH][QW] f32
+    static constexpr int OFF_LABL = align128(OFF_Q + NPLANES * QN * 4);          // [2][LH][LW] f32  L
+    static constexpr int OFF_LABAB = OFF_LABL + 2 * LH * LW * 4;                 // [2][LH][LW] u32  a|b<<16
+    static constexpr int OFF_CAND = align128(OFF_LABAB + 2 * LH * LW * 4);       // [4][TH][TW] f32  RH,BH,RV,BV
+    static constexpr int SMEM_BYTES = align128(OFF_CAND + 4 * TH * TW * 4);
+    static constexpr int OFF_OUT = OFF_LABL;       // [3][TH][TW] f32 output tile: aliases Lab (dead after phase 3)
+    static constexpr int OFF_CNT = OFF_Q + P_DHR * QN * 4;   // [CH][CW] u8: aliases the D planes (dead after phase 2)
+    static_assert(TW % 4 == 0 && TH % 2 == 0, "tile must be quad aligned (and 16-byte rows)");
+    static_assert(3 * ((TH * TW * 4 + 127) / 128 * 128) <= 4 * LH * LW * 4, "output tile must fit in the Lab region");
+    static_assert(CH * CW <= 4 * QN * 4, "count plane must fit in the D planes");
 };
 
-// ---- phase 0 ------------------------------------------------------------------------------------------
-PYSP_HD float load_site(const SelectParams& p, int y, int x) {
-    // (y,x): logical in-frame coordinate -> normalised, white-balanced photosite value
-    int sy = p.g.flip_y ? p.g.H - 1 - y : y;
-    int sx = p.g.flip_x ? p.g.W - 1 - x : x;
-    float s;
-    const char* row = (const char*)p.in + (long long)(sy - p.in_row0) * p.in_pitch;
-    if (p.in_kind == IN_U16) {
-        int pos = ((sy & 1) << 1) | (sx & 1);
-        float v = (float)pysp_ldg((const uint16_t*)row + sx);
-        float t = fminf(fmaxf(v - p.black[pos], 0.0f), p.white[pos]);
-        s = t / p.white[pos];
+// floats between the three planes of an output staging tile in planes mode (TMA sources are 128-byte aligned)
+template <int TW, int TH>
+struct OutPlane { static constexpr int FLOATS = (TH * TW * 4 + 127) / 128 * 32; };
+
+// stored-orientation origin of the raw input box of a tile, in elements of the held view
+template <int TW, int TH>
+PYSP_HD void select_input_box(const SelectParams& p, int tile_x, int tile_y, int* bx, int* by) {
+    typedef SelectTile<TW, TH> L;
+    const int x0 = tile_x * TW - 6, y0 = p.y_begin + tile_y * TH - 6;          // logical
+    *bx = p.g.flip_x ? p.g.W - (x0 + L::BOXW) : x0;
+    *by = (p.g.flip_y ? p.g.H - (y0 + L::BOXH) : y0) - p.in_row0;
+}
+
+// origin of the output tile in the destination views; returns the box width in elements
+template <int TW, int TH>
+PYSP_HD void tile_output_box(const StoreParams& st, const FrameGeom& g, int x0, int y0, int* bx, int* by) {
+    if (st.mode == OUT_FINAL) {
+        *bx = 3 * (g.flip_x ? g.W - (x0 + TW) : x0);
+        *by = (g.flip_y ? g.H - (y0 + TH) : y0) - st.img_row0;
     } else {
-        s = pysp_ldg((const float*)row + sx);
+        *bx = x0;
+        *by = y0 - st.plane_row0;
     }
-    int ch = (y & 1) + (x & 1);                     // R:0  G:1  B:2
-    return s * p.c.wb[ch];
+}
+
+// write one finished pixel into the output staging tile ([TH][3*TW] interleaved in stored orientation, or three
+// [TH][TW] planes r-g, b-g, g in logical orientation)
+template <int TW, int TH>
+PYSP_HD void stage_pixel(float* out, const StoreParams& st, const FrameGeom& g, const ColorParams& c, int ty, int tx, Rgb v) {
+    if (st.mode == OUT_FINAL) {
+        v = finish_pixel(c, st.kind, v);
+        int sy = g.flip_y ? TH - 1 - ty : ty, sx = g.flip_x ? TW - 1 - tx : tx;
+        float* o = out + (sy * TW + sx) * 3;
+        o[0] = v.r; o[1] = v.g; o[2] = v.b;
+    } else {
+        int o = ty * TW + tx;
+        constexpr int PS = OutPlane<TW, TH>::FLOATS;
+        out[o] = v.r - v.g; out[PS + o] = v.b - v.g; out[2 * PS + o] = v.g;
+    }
+}
+
+// generic (non-TMA) store of the staging tile, clipped to the destination views; converts to half if asked
+template <int TW, int TH>
+PYSP_HD void store_tile_generic(const float* out, const StoreParams& st, const FrameGeom& g, int x0, int y0) {
+    int bx, by;
+    tile_output_box<TW, TH>(st, g, x0, y0, &bx, &by);
+    if (st.mode == OUT_FINAL) {
+        if (st.kind == OUT_LIN_F16) {
+#ifndef PYSP_HOST_EMU
+            PYSP_ITEMS(i, TH * TW * 3) {
+                int r = i / (TW * 3), cc = i - r * (TW * 3);
+                int gy = by + r, gx = bx + cc;
+                if (gy >= 0 && gy < st.img.rows && gx >= 0 && gx < st.img.cols)
+                    *(__half*)((char*)st.img.base + (long long)gy * st.img.pitch + (long long)gx * 2) = __float2half_rn(out[i]);
+            }
+#endif
+        } else {
+            box_store_generic(out, st.img, bx, by, TW * 3, TH);
+        }
+    } else {
+        for (int k = 0; k < 3; ++k) box_store_generic(out + k * OutPlane<TW, TH>::FLOATS, st.plane[k], bx, by, TW, TH);
+    }
 }
 
 // 5 taps, strictly left to right (ahd.py:97-102)
@@ -132,40 +188,62 @@ PYSP_HD void up_br(const float v[3][3], float o[4]) {
 
 PYSP_HD float gauss_row(float l, float c, float r) { return (PYSP_GK1 * c) + (PYSP_GK0 * (l + r)); }
 
+// ---- phase 0: staging box -> normalised, white-balanced quarter planes -------------------------------------
 template <int TW, int TH, bool EDGE>
-PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_x, int tile_y) {
+PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
+    typedef SelectTile<TW, TH> L;
+    constexpr int QW = L::QW, QN = L::QN;
+    const int H = p.g.H, W = p.g.W;
+    const int bx0 = tile_x * TW - 6, by0 = p.y_begin + tile_y * TH - 6;       // logical origin of the box
+    float* Q = (float*)(smem + L::OFF_Q);
+    const void* stage = smem + L::OFF_STAGE;
+    PYSP_ITEMS(it, QN) {
+        int qy = it / QW, qx = it - qy * QW;
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int ly = 2 * qy + (k >> 1), lx = 2 * qx + (k & 1);                // local logical coords in the box
+            int y = by0 + ly, x = bx0 + lx;
+            if (EDGE) {
+                y = phase_clamp(y, H); x = phase_clamp(x, W);
+                ly = y - by0; lx = x - bx0;
+            }
+            int sly = p.g.flip_y ? L::BOXH - 1 - ly : ly, slx = p.g.flip_x ? L::BOXW - 1 - lx : lx;
+            int si = sly * L::BOXW + slx;
+            float s;
+            if (p.in_kind == IN_U16) {
+                int sy = p.g.flip_y ? H - 1 - y : y, sx = p.g.flip_x ? W - 1 - x : x;   // stored parity picks the level
+                int pos = ((sy & 1) << 1) | (sx & 1);
+                float raw = (float)((const uint16_t*)stage)[si];
+                float t = fminf(fmaxf(raw - p.black[pos], 0.0f), p.white[pos]);
+                s = t / p.white[pos];
+            } else {
+                s = ((const float*)stage)[si];
+            }
+            v[k] = s * p.c.wb[(k >> 1) + (k & 1)];                          // R:0  G:1  B:2
+        }
+        Q[L::P_R * QN + it] = v[0]; Q[L::P_G1 * QN + it] = v[1];
+        Q[L::P_G2 * QN + it] = v[2]; Q[L::P_B * QN + it] = v[3];
+    }
+}
+
+// ---- phases 1..4 ---------------------------------------------------------------------------------------------
+// `before_out` is called by every thread after phase 3 and before the barrier that precedes the first write
+// to the output staging tile (the device pipeline waits there for the previous tile's TMA store).
+template <int TW, int TH, bool EDGE, typename BeforeOut>
+PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int tile_x, int tile_y, BeforeOut before_out) {
     typedef SelectTile<TW, TH> L;
     constexpr int QW = L::QW, QH = L::QH, QN = L::QN;
     const int H = p.g.H, W = p.g.W;
     const int hq = H >> 1, wq = W >> 1;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;     // logical origin of the output tile (even)
     const int qx0 = (x0 >> 1) - 3, qy0 = (y0 >> 1) - 3;           // quarter-plane origin
-    float* Q = sm + L::OFF_Q;
-    float* labL = sm + L::OFF_LABL;
-    uint32_t* labAB = (uint32_t*)(sm + L::OFF_LABAB);
-    float* cand = sm + L::OFF_CAND;
-    uint8_t* cnt = (uint8_t*)(sm + L::OFF_CNT);
-
-    // ---------------- phase 0: load, normalise, white balance -> quarter planes --------------------------
-    PYSP_ITEMS(it, QN * 2) {
-        // one item = the two horizontally adjacent sites (even,odd column) of one mosaic row
-        int ly = it / QW, qx = it - ly * QW;          // ly: local full-res row 0..2*QH-1
-        int y = 2 * qy0 + ly, x = 2 * (qx0 + qx);
-        int yy = y, xa = x, xb = x + 1;
-        bool ok = true;
-        if (EDGE) {
-            yy = phase_clamp(y, H); xa = phase_clamp(x, W); xb = phase_clamp(x + 1, W);
-            // rows of the frame that this band's buffer does not hold are never consumed
-            int sy = p.g.flip_y ? H - 1 - yy : yy;
-            ok = sy >= p.in_row0 && sy < p.in_row1;
-        }
-        float va = 0.0f, vb = 0.0f;
-        if (ok) { va = load_site(p, yy, xa); vb = load_site(p, yy, xb); }
-        int qi = (ly >> 1) * QW + qx;
-        if (ly & 1) { Q[L::P_G2 * QN + qi] = va; Q[L::P_B * QN + qi] = vb; }
-        else        { Q[L::P_R * QN + qi] = va; Q[L::P_G1 * QN + qi] = vb; }
-    }
-    PYSP_SYNC();
+    float* Q = (float*)(smem + L::OFF_Q);
+    float* labL = (float*)(smem + L::OFF_LABL);
+    uint32_t* labAB = (uint32_t*)(smem + L::OFF_LABAB);
+    float* cand = (float*)(smem + L::OFF_CAND);
+    uint8_t* cnt = (uint8_t*)(smem + L::OFF_CNT);
+    float* out = (float*)(smem + L::OFF_OUT);
 
     // ---------------- phase 1: directional greens and colour differences at R/B sites ---------------------
     {
@@ -230,8 +308,6 @@ PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_
                 // cell is static; only its quarter index moves at the frame border.
                 float gw[4][4];
                 {
-                    // quarter indices of window rows/cols: row -1 -> odd row of quad i-1, rows 0,1 -> quad i,
-                    // row 2 -> even row of quad i+1
                     int wr[4], wc[4];
                     if (EDGE) {
 #pragma unroll
@@ -299,6 +375,8 @@ PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_
     PYSP_SYNC();
 
     // ---------------- phase 3: homogeneity counts for the tile + 1 px ---------------------------------------
+    // The centre and the two neighbours along the direction always pass both tests (their distances define
+    // eps_l and eps_c), so only the six other window cells are tested: count = 3 + passes.
     {
         constexpr int BW = L::CW / 2, BH = L::CH / 2;
         PYSP_ITEMS(it, BW * BH) {
@@ -337,11 +415,12 @@ PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_
                     float da1 = a0 - wa[a1][b1], db1 = b0 - wb[a1][b1];
                     float da2 = a0 - wa[a2][b2], db2 = b0 - wb[a2][b2];
                     float epsc = fmaxf((da1 * da1) + (db1 * db1), (da2 * da2) + (db2 * db2));
-                    int n = 0;
+                    int n = 3;
 #pragma unroll
                     for (int u = -1; u <= 1; ++u)
 #pragma unroll
                         for (int v = -1; v <= 1; ++v) {
+                            if ((dir ? v : u) == 0) continue;                  // centre + the two eps-defining cells
                             float dl = wl[a + u][b + v] - l0;                  // signed (pyx:56)
                             float da = wa[a + u][b + v] - a0, db = wb[a + u][b + v] - b0;
                             float d2 = (da * da) + (db * db);
@@ -354,16 +433,17 @@ PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_
             for (int k = 0; k < 4; ++k) cnt[(cy + (k >> 1)) * L::CW + cx + (k & 1)] = (uint8_t)res[k];
         }
     }
+    before_out();
     PYSP_SYNC();
 
-    // ---------------- phase 4: 3x3 vote, select, epilogue, store ----------------------------------------------
+    // ---------------- phase 4: 3x3 vote, select, epilogue -> output staging tile ---------------------------
     {
         constexpr int OW = TW / 2, OH = TH / 2;
         PYSP_ITEMS(it, OW * OH) {
             int oy = it / OW, ox = it - oy * OW;
             int ty = 2 * oy, tx = 2 * ox;                 // tile coords of the quad
             int fy = y0 + ty, fx = x0 + tx;
-            if (fy >= p.y_end || fx >= W) continue;       // partial tile (even dims: whole quad in or out)
+            if (EDGE) { if (fy >= H || fx >= W) continue; }       // partial tile (even dims: whole quad in or out)
             int wy[4], wx[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -396,25 +476,16 @@ PYSP_D void select_tile(const SelectParams& p, float* __restrict__ sm, int tile_
                 else if (k == 1) v.g = Q[L::P_G1 * QN + qi];
                 else if (k == 2) v.g = Q[L::P_G2 * QN + qi];
                 else v.g = pick_h ? Q[L::P_GHB * QN + qi] : Q[L::P_GVB * QN + qi];
-                v = finish_pixel(p.c, p.out_kind, v);
-                int yy = fy + a, xx = fx + b;
-                if (p.store_flip) {                       // stored orientation (image.py:181)
-                    if (p.g.flip_y) yy = H - 1 - yy;
-                    if (p.g.flip_x) xx = W - 1 - xx;
-                }
-                char* row = (char*)p.out + (long long)(yy - p.out_row0) * p.out_pitch;
-                if (p.out_kind == OUT_LIN_F16) {
-#ifndef PYSP_HOST_EMU
-                    __half* o16 = (__half*)row + 3 * (long long)xx;
-                    o16[0] = __float2half_rn(v.r); o16[1] = __float2half_rn(v.g); o16[2] = __float2half_rn(v.b);
-#endif
-                } else {
-                    float* o32 = (float*)row + 3 * (long long)xx;
-                    o32[0] = v.r; o32[1] = v.g; o32[2] = v.b;
-                }
+                stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty + a, tx + b, v);
             }
         }
     }
+}
+
+template <int TW, int TH>
+PYSP_HD bool select_tile_is_edge(const SelectParams& p, int tile_x, int tile_y) {
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
+    return x0 < 6 || y0 < 6 || x0 + TW + 6 > p.g.W || y0 + TH + 6 > p.g.H;
 }
 
 }  // namespace pysp

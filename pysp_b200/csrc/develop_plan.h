@@ -1,6 +1,7 @@
 // Host-side planning of one pysp_develop call: argument validation, row ranges of every kernel in the
 // chain (K1 select, then one K2 median launch per stage, each shrinking the band by 4 rows per side),
-// scratch ping-pong.  Pure C++ (no CUDA calls) so that tests/host_emu can drive the same plan.
+// scratch ping-pong, the 2-D views every kernel loads from / stores to.  Pure C++ (no CUDA calls) so that
+// tests/host_emu can drive the same plan.
 #pragma once
 #include <stdarg.h>
 #include <stdio.h>
@@ -15,10 +16,8 @@ namespace pysp {
 
 struct DevelopPlan {
     SelectParams select;
-    int select_tiles;
     int n_stages;
     MedianParams median[PYSP_MAX_STAGES];
-    int median_tiles[PYSP_MAX_STAGES];
 };
 
 static inline int plan_fail(char* err, size_t n, int code, const char* fmt, ...) {
@@ -33,6 +32,10 @@ static inline int64_t develop_scratch_bytes(int32_t width, int32_t rows, int32_t
     if (stages <= 0) return 0;
     int64_t one = (int64_t)(rows + 8 * stages) * width * 3 * (int64_t)sizeof(float);
     return stages >= 2 ? 2 * one : one;
+}
+
+static inline bool tma_ok(const View2D& v) {
+    return ((uintptr_t)v.base % 16) == 0 && (v.pitch % 16) == 0 && v.rows > 0 && v.cols > 0;
 }
 
 static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int tw2, int th2, DevelopPlan* plan,
@@ -64,11 +67,11 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     if (S > PYSP_MAX_STAGES)
         return plan_fail(err, errn, PYSP_ERR_UNSUPPORTED, "pysp_develop: at most %d postprocess stages", PYSP_MAX_STAGES);
     const int64_t esz = a->in_kind == PYSP_IN_U16 ? 2 : 4;
-    if (a->in_pitch_bytes < W * esz || (a->in_pitch_bytes % esz))
-        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad in_pitch_bytes");
+    if (a->in_pitch_bytes < W * esz || (a->in_pitch_bytes % esz) || ((uintptr_t)a->in % esz))
+        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad input pitch/alignment");
     const int64_t osz = a->out_kind == PYSP_OUT_LIN_F16 ? 2 : 4;
-    if (a->out_pitch_bytes < 3 * W * osz || (a->out_pitch_bytes % osz))
-        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad out_pitch_bytes");
+    if (a->out_pitch_bytes < 3 * W * osz || (a->out_pitch_bytes % osz) || ((uintptr_t)a->out % osz))
+        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad output pitch/alignment");
     // logical (RGGB-oriented) rows of the band
     const int lb = flip_y ? H - re : rb, le = flip_y ? H - rb : re;
     auto lo = [&](int v) { return v < 0 ? 0 : v; };
@@ -83,8 +86,8 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
                              a->in_row0 + a->in_rows, sb, se, 6 + 4 * S);
     }
     const int64_t need = develop_scratch_bytes(W, re - rb, S);
-    if (S > 0 && (!a->scratch || a->scratch_bytes < need))
-        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: scratch of %lld bytes needed", (long long)need);
+    if (S > 0 && (!a->scratch || a->scratch_bytes < need || ((uintptr_t)a->scratch % 4)))
+        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: 4-byte aligned scratch of %lld bytes needed", (long long)need);
 
     ColorParams c;
     memset(&c, 0, sizeof(c));
@@ -95,42 +98,50 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     FrameGeom g = {H, W, flip_y, flip_x};
 
     const int64_t scratch_rows = (re - rb) + 8 * S;
-    float* sbuf[2] = {(float*)a->scratch, S >= 2 ? (float*)a->scratch + scratch_rows * W * 3 : nullptr};
-    const long long spitch = (long long)W * 3 * sizeof(float);
+    auto final_store = [&](StoreParams& st) {
+        st.mode = OUT_FINAL; st.kind = a->out_kind;
+        st.img.base = (char*)a->out + (int64_t)(rb - a->out_row0) * a->out_pitch_bytes;
+        st.img.pitch = a->out_pitch_bytes; st.img.rows = re - rb; st.img.cols = 3 * W; st.img.elem = (int)osz;
+        st.img_row0 = rb;
+        st.tma = a->out_kind != PYSP_OUT_LIN_F16 && tma_ok(st.img);
+    };
+    auto plane_store = [&](StoreParams& st, int buf, int row0, int rows) {
+        st.mode = OUT_PLANES; st.kind = OUT_CAM_F32;
+        st.tma = 1;
+        for (int k = 0; k < 3; ++k) {
+            st.plane[k].base = (float*)a->scratch + ((int64_t)buf * 3 + k) * scratch_rows * W;
+            st.plane[k].pitch = (long long)W * 4; st.plane[k].rows = rows; st.plane[k].cols = W; st.plane[k].elem = 4;
+            st.tma = st.tma && tma_ok(st.plane[k]);
+        }
+        st.plane_row0 = row0;
+    };
 
     memset(plan, 0, sizeof(*plan));
     SelectParams& sp = plan->select;
     sp.g = g; sp.c = c;
-    sp.in_kind = a->in_kind; sp.in = a->in; sp.in_pitch = a->in_pitch_bytes;
-    sp.in_row0 = a->in_row0; sp.in_row1 = a->in_row0 + a->in_rows;
+    sp.in_kind = a->in_kind;
+    sp.in.base = (void*)a->in; sp.in.pitch = a->in_pitch_bytes; sp.in.rows = a->in_rows; sp.in.cols = W; sp.in.elem = (int)esz;
+    sp.in_row0 = a->in_row0;
+    sp.tma_in = tma_ok(sp.in);
     const int perm[4] = {0, 1, 3, 2};          // [TL,TR,BR,BL] -> index (sy&1)*2+(sx&1)
     for (int i = 0; i < 4; ++i) { sp.black[perm[i]] = a->black[i]; sp.white[perm[i]] = a->white[i]; }
     sp.lut = (const uint2*)a->lab_lut;
     sp.y_begin = k1b; sp.y_end = k1e;
     sp.tiles_x = (W + tw1 - 1) / tw1;
-    if (S == 0) {
-        sp.out_kind = a->out_kind; sp.out = a->out; sp.out_pitch = a->out_pitch_bytes; sp.out_row0 = a->out_row0;
-        sp.store_flip = 1;
-    } else {
-        sp.out_kind = OUT_CAM_F32; sp.out = sbuf[0]; sp.out_pitch = spitch; sp.out_row0 = k1b; sp.store_flip = 0;
-    }
-    plan->select_tiles = sp.tiles_x * ((k1e - k1b + th1 - 1) / th1);
+    sp.n_tiles = sp.tiles_x * ((k1e - k1b + th1 - 1) / th1);
+    if (S == 0) final_store(sp.st); else plane_store(sp.st, 0, k1b, k1e - k1b);
     plan->n_stages = S;
-    int prev_b = k1b, prev_e = k1e;
     for (int s = 1; s <= S; ++s) {
         MedianParams& mp = plan->median[s - 1];
+        const StoreParams& prev = s == 1 ? sp.st : plan->median[s - 2].st;
         mp.g = g; mp.c = c;
-        mp.in = sbuf[(s - 1) & 1]; mp.in_pitch = spitch; mp.in_row0 = prev_b; mp.in_row1 = prev_e;
+        for (int k = 0; k < 3; ++k) mp.in[k] = prev.plane[k];
+        mp.in_row0 = prev.plane_row0;
+        mp.tma_in = prev.tma;
         mp.y_begin = lo(lb - 4 * (S - s)); mp.y_end = hi(le + 4 * (S - s));
         mp.tiles_x = (W + tw2 - 1) / tw2;
-        if (s == S) {
-            mp.out_kind = a->out_kind; mp.out = a->out; mp.out_pitch = a->out_pitch_bytes; mp.out_row0 = a->out_row0;
-            mp.store_flip = 1;
-        } else {
-            mp.out_kind = OUT_CAM_F32; mp.out = sbuf[s & 1]; mp.out_pitch = spitch; mp.out_row0 = mp.y_begin; mp.store_flip = 0;
-        }
-        plan->median_tiles[s - 1] = mp.tiles_x * ((mp.y_end - mp.y_begin + th2 - 1) / th2);
-        prev_b = mp.y_begin; prev_e = mp.y_end;
+        mp.n_tiles = mp.tiles_x * ((mp.y_end - mp.y_begin + th2 - 1) / th2);
+        if (s == S) final_store(mp.st); else plane_store(mp.st, s & 1, mp.y_begin, mp.y_end - mp.y_begin);
     }
     return PYSP_OK;
 }

@@ -2,13 +2,16 @@
 //     r' = med5(r-g)+g ; b' = med5(b-g)+g ; g' = (((med5(g-r') + med5(g-b')) + r') + b') / 2
 // cv2.medianBlur(f32, 5): exact 5x5 selection, BORDER_REPLICATE.
 //
-// One CTA produces a TW x TH tile from the tile + 4 px: phase A forms the two colour-difference planes
-// in shared memory, phase B takes their medians on the tile + 2 px and forms the second pair of
-// difference planes, phase C takes those medians on the tile and runs the output epilogue (clip, float64
-// camera->linear-sRGB matrix, optional gamma) when this is the last stage, so the final image is written
-// exactly once.
+// The previous kernel of the chain hands over three float planes r-g, b-g, g (see StoreParams), so the
+// tile + 4 px box of each plane is fetched by TMA straight into the shared-memory planes the medians read
+// (the next tile's boxes are prefetched while the current tile is in phase C).  Phase B takes the medians
+// on the tile + 2 px and forms the second pair of difference planes, phase C takes those medians on the tile
+// and runs the output epilogue (clip, float64 camera->linear-sRGB matrix, optional gamma) when this is the last
+// stage, so the final image is written exactly once.
 #pragma once
 #include "pysp_common.cuh"
+#include "ahd_select.cuh"   // stage_pixel / store_tile_generic / tile_output_box
+#include "tma.cuh"
 
 namespace pysp {
 
@@ -39,53 +42,64 @@ PYSP_HD float median25(float p[25]) {
 template <int TW_, int TH_>
 struct MedianTile {
     static constexpr int TW = TW_, TH = TH_;
-    static constexpr int AW = TW + 8, AH = TH + 8;     // input region (tile + 4)
+    static constexpr int AW = TW + 8, AH = TH + 8;     // input box (tile + 4)
     static constexpr int BW = TW + 4, BH = TH + 4;     // first-median region (tile + 2)
-    static constexpr int OFF_DR = 0;                   // [AH][AW] r-g
-    static constexpr int OFF_DB = OFF_DR + AH * AW;    // [AH][AW] b-g
-    static constexpr int OFF_G = OFF_DB + AH * AW;     // [AH][AW] g
-    static constexpr int OFF_ER = OFF_G + AH * AW;     // [BH][BW] g-r'
-    static constexpr int OFF_EB = OFF_ER + BH * BW;    // [BH][BW] g-b'
-    static constexpr int OFF_RP = OFF_EB + BH * BW;    // [TH][TW] r'
-    static constexpr int OFF_BP = OFF_RP + TH * TW;    // [TH][TW] b'
-    static constexpr int SMEM_BYTES = (OFF_BP + TH * TW) * 4;
+    static constexpr int align128(int v) { return (v + 127) / 128 * 128; }
+    static constexpr int PLANE_BYTES = align128(AH * AW * 4);
+    static constexpr int OFF_BAR = 0;
+    static constexpr int OFF_IN = 128;                                  // 3 x [AH][AW] f32: r-g, b-g, g (TMA destination)
+    static constexpr int OFF_ER = align128(OFF_IN + 3 * PLANE_BYTES);   // [BH][BW] g-r'
+    static constexpr int OFF_EB = OFF_ER + BH * BW * 4;                 // [BH][BW] g-b'
+    static constexpr int OFF_RP = OFF_EB + BH * BW * 4;                 // [TH][TW] r'
+    static constexpr int OFF_BP = OFF_RP + TH * TW * 4;                 // [TH][TW] b'
+    static constexpr int OFF_OUT = align128(OFF_BP + TH * TW * 4);      // [3][TH][TW] output staging tile
+    static constexpr int SMEM_BYTES = align128(OFF_OUT + 3 * align128(TH * TW * 4));
+    static_assert(TW % 4 == 0, "16-byte rows");
 };
 
+template <int TW, int TH>
+PYSP_HD bool median_tile_is_edge(const MedianParams& p, int tile_x, int tile_y) {
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
+    return x0 < 4 || y0 < 4 || x0 + TW + 4 > p.g.W || y0 + TH + 4 > p.g.H;
+}
+
+// phase A (edge tiles only): the box arrives zero-filled outside the frame; REPLICATE needs the value of the
+// clamped in-frame cell, which is always inside the same box
+template <int TW, int TH>
+PYSP_D void median_fix_border(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
+    typedef MedianTile<TW, TH> L;
+    const int H = p.g.H, W = p.g.W;
+    const int bx0 = tile_x * TW - 4, by0 = p.y_begin + tile_y * TH - 4;
+    PYSP_ITEMS(it, L::AW * L::AH) {
+        int ly = it / L::AW, lx = it - ly * L::AW;
+        int y = by0 + ly, x = bx0 + lx;
+        if (y >= 0 && y < H && x >= 0 && x < W) continue;
+        int src = (clampi(y, H) - by0) * L::AW + (clampi(x, W) - bx0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float* pl = (float*)(smem + L::OFF_IN + k * L::PLANE_BYTES);
+            pl[it] = pl[src];
+        }
+    }
+}
+
+// phase B: r', b' and the second difference planes on the tile + 2 px
 template <int TW, int TH, bool EDGE>
-PYSP_D void median_tile(const MedianParams& p, float* __restrict__ sm, int tile_x, int tile_y) {
+PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
     typedef MedianTile<TW, TH> L;
     const int H = p.g.H, W = p.g.W;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
-    float* DR = sm + L::OFF_DR; float* DB = sm + L::OFF_DB; float* G = sm + L::OFF_G;
-    float* ER = sm + L::OFF_ER; float* EB = sm + L::OFF_EB;
-    float* RP = sm + L::OFF_RP; float* BP = sm + L::OFF_BP;
-
-    // ---- phase A: colour differences on the tile + 4 px (REPLICATE at the frame border) -----------------
-    PYSP_ITEMS(it, L::AW * L::AH) {
-        int ly = it / L::AW, lx = it - ly * L::AW;
-        int y = y0 - 4 + ly, x = x0 - 4 + lx;
-        float r = 0.f, g = 0.f, b = 0.f;
-        bool ok = true;
-        if (EDGE) {
-            y = clampi(y, H); x = clampi(x, W);
-            ok = y >= p.in_row0 && y < p.in_row1;       // rows this band's buffer does not hold are never consumed
-        }
-        if (ok) {
-            const float* src = (const float*)((const char*)p.in + (long long)(y - p.in_row0) * p.in_pitch) + 3 * (long long)x;
-            r = pysp_ldg(src); g = pysp_ldg(src + 1); b = pysp_ldg(src + 2);
-        }
-        DR[it] = r - g; DB[it] = b - g; G[it] = g;
-    }
-    PYSP_SYNC();
-
-    // ---- phase B: r', b' and the second difference planes on the tile + 2 px ----------------------------
+    const float* DR = (const float*)(smem + L::OFF_IN);
+    const float* DB = (const float*)(smem + L::OFF_IN + L::PLANE_BYTES);
+    const float* G = (const float*)(smem + L::OFF_IN + 2 * L::PLANE_BYTES);
+    float* ER = (float*)(smem + L::OFF_ER); float* EB = (float*)(smem + L::OFF_EB);
+    float* RP = (float*)(smem + L::OFF_RP); float* BP = (float*)(smem + L::OFF_BP);
     PYSP_ITEMS(it, L::BW * L::BH) {
         int ly = it / L::BW, lx = it - ly * L::BW;
         int y = y0 - 2 + ly, x = x0 - 2 + lx;
         if (EDGE) { if (y < 0 || y >= H || x < 0 || x >= W) continue; }
+        // the input planes hold the REPLICATE extension, so the window around an in-frame pixel is final
         float wr[25], wb[25];
-        // the input region was filled through the clamp, so a window taken around an in-frame pixel is
-        // already the REPLICATE window
         int c = (ly + 2) * L::AW + lx + 2;
 #pragma unroll
         for (int u = 0; u < 5; ++u)
@@ -101,13 +115,23 @@ PYSP_D void median_tile(const MedianParams& p, float* __restrict__ sm, int tile_
         int ty = ly - 2, tx = lx - 2;
         if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { RP[ty * TW + tx] = r1; BP[ty * TW + tx] = b1; }
     }
-    PYSP_SYNC();
+}
 
-    // ---- phase C: g' on the tile, epilogue, store --------------------------------------------------------
+// phase C: g' on the tile, epilogue -> output staging tile
+template <int TW, int TH, bool EDGE>
+PYSP_D void median_phase_c(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
+    typedef MedianTile<TW, TH> L;
+    const int H = p.g.H, W = p.g.W;
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
+    const float* G = (const float*)(smem + L::OFF_IN + 2 * L::PLANE_BYTES);
+    const float* ER = (const float*)(smem + L::OFF_ER); const float* EB = (const float*)(smem + L::OFF_EB);
+    const float* RP = (const float*)(smem + L::OFF_RP); const float* BP = (const float*)(smem + L::OFF_BP);
+    float* out = (float*)(smem + L::OFF_OUT);
+    (void)G;
     PYSP_ITEMS(it, TW * TH) {
         int ty = it / TW, tx = it - ty * TW;
         int y = y0 + ty, x = x0 + tx;
-        if (y >= p.y_end || x >= W) continue;
+        if (EDGE) { if (y >= H || x >= W) continue; }
         float wr[25], wb[25];
 #pragma unroll
         for (int u = 0; u < 5; ++u)
@@ -121,22 +145,7 @@ PYSP_D void median_tile(const MedianParams& p, float* __restrict__ sm, int tile_
         Rgb v;
         v.r = r1; v.b = b1;
         v.g = (((median25(wr) + median25(wb)) + r1) + b1) / 2.0f;
-        v = finish_pixel(p.c, p.out_kind, v);
-        int yy = y, xx = x;
-        if (p.store_flip) {
-            if (p.g.flip_y) yy = H - 1 - yy;
-            if (p.g.flip_x) xx = W - 1 - xx;
-        }
-        char* row = (char*)p.out + (long long)(yy - p.out_row0) * p.out_pitch;
-        if (p.out_kind == OUT_LIN_F16) {
-#ifndef PYSP_HOST_EMU
-            __half* o16 = (__half*)row + 3 * (long long)xx;
-            o16[0] = __float2half_rn(v.r); o16[1] = __float2half_rn(v.g); o16[2] = __float2half_rn(v.b);
-#endif
-        } else {
-            float* o32 = (float*)row + 3 * (long long)xx;
-            o32[0] = v.r; o32[1] = v.g; o32[2] = v.b;
-        }
+        stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty, tx, v);
     }
 }
 

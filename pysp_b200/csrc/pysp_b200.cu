@@ -1,4 +1,5 @@
 // libpysp_b200.so: kernels + C ABI (include/pysp_b200.h).  sm_100a only, no CPU path.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -19,22 +20,134 @@ namespace pysp {
 constexpr int K1_TW = 60, K1_TH = 28, K1_THREADS = 256;
 constexpr int K2_TW = 60, K2_TH = 28, K2_THREADS = 256;
 
-__global__ void __launch_bounds__(K1_THREADS, 2) ahd_select_kernel(const __grid_constant__ SelectParams p) {
-    extern __shared__ __align__(16) float smem[];
-    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
-    const int x0 = tile_x * K1_TW, y0 = p.y_begin + tile_y * K1_TH;
-    const bool edge = x0 < 6 || y0 < 6 || x0 + K1_TW + 6 > p.g.W || y0 + K1_TH + 6 > p.g.H || y0 + K1_TH > p.y_end;
-    if (edge) select_tile<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y);
-    else select_tile<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y);
+struct OutMaps { CUtensorMap m[3]; };     // final image: m[0]; planes: m[0..2]
+
+// stage-out: TMA store of the finished staging tile (one elected thread), or the generic clipped store
+template <int TW, int TH>
+__device__ __forceinline__ void store_tile(const float* out, const StoreParams& st, const FrameGeom& g, const OutMaps& maps,
+                                           int x0, int y0) {
+    if (st.tma) {
+        if (threadIdx.x == 0) {
+            int bx, by;
+            tile_output_box<TW, TH>(st, g, x0, y0, &bx, &by);
+            if (st.mode == OUT_FINAL) {
+                tma_store_2d(out, &maps.m[0], bx, by);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tma_store_2d(out + k * OutPlane<TW, TH>::FLOATS, &maps.m[k], bx, by);
+            }
+            tma_store_commit();
+        }
+    } else {
+        store_tile_generic<TW, TH>(out, st, g, x0, y0);
+    }
 }
 
-__global__ void __launch_bounds__(K2_THREADS, 2) median_stage_kernel(const __grid_constant__ MedianParams p) {
-    extern __shared__ __align__(16) float smem[];
-    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
-    const int x0 = tile_x * K2_TW, y0 = p.y_begin + tile_y * K2_TH;
-    const bool edge = x0 < 4 || y0 < 4 || x0 + K2_TW + 4 > p.g.W || y0 + K2_TH + 4 > p.g.H || y0 + K2_TH > p.y_end;
-    if (edge) median_tile<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
-    else median_tile<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
+// K1, persistent: grid = resident CTAs; each CTA walks tiles blockIdx.x, +gridDim.x, ...  The raw box of the next
+// tile is in flight (TMA -> staging, mbarrier) while phases 1-4 of the current tile run; the finished tile leaves
+// through the staging tile by TMA store, overlapped with the next tile's phases 0-3.
+__global__ void __launch_bounds__(K1_THREADS, 2)
+ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant__ CUtensorMap in_map,
+                  const __grid_constant__ OutMaps out_maps) {
+    typedef SelectTile<K1_TW, K1_TH> L;
+    extern __shared__ __align__(128) char smem[];
+    uint64_t* bar = (uint64_t*)(smem + L::OFF_BAR);
+    void* stage = smem + L::OFF_STAGE;
+    const uint32_t box_bytes = L::BOXW * L::BOXH * (p.in_kind == IN_U16 ? 2 : 4);
+    int tile = blockIdx.x;
+    uint32_t parity = 0;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto fetch = [&](int t) {       // start (TMA) or perform (generic) the load of tile t's raw box
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        int bx, by;
+        select_input_box<K1_TW, K1_TH>(p, tx, ty, &bx, &by);
+        if (p.tma_in) {
+            if (threadIdx.x == 0) {
+                fence_async_smem();
+                mbar_expect_tx(bar, box_bytes);
+                tma_load_2d(stage, &in_map, bx, by, bar);
+            }
+        } else {
+            box_load_generic(stage, p.in, bx, by, L::BOXW, L::BOXH);
+        }
+    };
+    if (tile < p.n_tiles) fetch(tile);
+    if (!p.tma_in) __syncthreads();
+    for (; tile < p.n_tiles; tile += gridDim.x) {
+        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+        const bool edge = select_tile_is_edge<K1_TW, K1_TH>(p, tile_x, tile_y);
+        if (p.tma_in) { mbar_wait(bar, parity); parity ^= 1; }
+        if (edge) select_phase0<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y);
+        else select_phase0<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y);
+        __syncthreads();                                  // staging consumed, quarter planes complete
+        const int next = tile + gridDim.x;
+        if (p.tma_in && next < p.n_tiles) fetch(next);
+        auto before_out = [&]() { if (p.st.tma && threadIdx.x == 0) tma_store_wait_read(); };
+        if (edge) select_phases<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y, before_out);
+        else select_phases<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y, before_out);
+        if (p.st.tma) fence_async_smem();                 // staging tile written by the generic proxy, read by TMA
+        __syncthreads();
+        store_tile<K1_TW, K1_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K1_TW,
+                                 p.y_begin + tile_y * K1_TH);
+        if (!p.tma_in && next < p.n_tiles) fetch(next);
+        __syncthreads();                                  // planes free for the next tile; generic store/load done
+    }
+    if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();
+}
+
+// K2, persistent, same pipeline: the three input planes of the next tile are fetched by TMA while phase C runs.
+__global__ void __launch_bounds__(K2_THREADS, 2)
+median_stage_kernel(const __grid_constant__ MedianParams p, const __grid_constant__ OutMaps in_maps,
+                    const __grid_constant__ OutMaps out_maps) {
+    typedef MedianTile<K2_TW, K2_TH> L;
+    extern __shared__ __align__(128) char smem[];
+    uint64_t* bar = (uint64_t*)(smem + L::OFF_BAR);
+    int tile = blockIdx.x;
+    uint32_t parity = 0;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto fetch = [&](int t) {
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int bx = tx * K2_TW - 4, by = p.y_begin + ty * K2_TH - 4 - p.in_row0;
+        if (p.tma_in) {
+            if (threadIdx.x == 0) {
+                fence_async_smem();
+                mbar_expect_tx(bar, 3 * L::AW * L::AH * 4);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) tma_load_2d(smem + L::OFF_IN + k * L::PLANE_BYTES, &in_maps.m[k], bx, by, bar);
+            }
+        } else {
+            for (int k = 0; k < 3; ++k) box_load_generic(smem + L::OFF_IN + k * L::PLANE_BYTES, p.in[k], bx, by, L::AW, L::AH);
+        }
+    };
+    if (tile < p.n_tiles) fetch(tile);
+    if (!p.tma_in) __syncthreads();
+    for (; tile < p.n_tiles; tile += gridDim.x) {
+        const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+        const bool edge = median_tile_is_edge<K2_TW, K2_TH>(p, tile_x, tile_y);
+        if (p.tma_in) { mbar_wait(bar, parity); parity ^= 1; }
+        if (edge) {
+            median_fix_border<K2_TW, K2_TH>(p, smem, tile_x, tile_y);
+            __syncthreads();
+            median_phase_b<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
+        } else {
+            median_phase_b<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
+        }
+        if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();     // previous tile's store has read the staging tile
+        __syncthreads();                                             // input planes consumed
+        const int next = tile + gridDim.x;
+        if (p.tma_in && next < p.n_tiles) fetch(next);
+        if (edge) median_phase_c<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
+        else median_phase_c<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
+        if (p.st.tma) fence_async_smem();
+        __syncthreads();
+        store_tile<K2_TW, K2_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K2_TW,
+                                 p.y_begin + tile_y * K2_TH);
+        if (!p.tma_in && next < p.n_tiles) fetch(next);
+        __syncthreads();
+    }
+    if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();
 }
 
 }  // namespace pysp
@@ -141,6 +254,59 @@ int pysp_lab_lut_pack_host(const int16_t* lut, void* packed) {
     return PYSP_OK;
 }
 
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<EncodeTiledFn> cached{nullptr};
+    EncodeTiledFn f = cached.load();
+    if (f) return f;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return nullptr;
+    cached.store((EncodeTiledFn)sym);
+    return (EncodeTiledFn)sym;
+}
+
+static int make_map(CUtensorMap* m, const View2D& v, int box_w, int box_h) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(PYSP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)v.cols, (cuuint64_t)v.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)v.pitch};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, v.elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, v.base, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PYSP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%d view, pitch %lld", (int)r,
+                                       v.rows, v.cols, v.pitch);
+    return PYSP_OK;
+}
+
+static int make_out_maps(OutMaps* om, const StoreParams& st, int tw, int th) {
+    memset(om, 0, sizeof(*om));
+    if (!st.tma) return PYSP_OK;
+    if (st.mode == OUT_FINAL) return make_map(&om->m[0], st.img, 3 * tw, th);
+    for (int k = 0; k < 3; ++k) {
+        int rc = make_map(&om->m[k], st.plane[k], tw, th);
+        if (rc) return rc;
+    }
+    return PYSP_OK;
+}
+
+static int resident_ctas(const void* kernel, int threads, int smem_bytes, int* out) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes);
+    if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if (per_sm < 1) return fail(PYSP_ERR_CUDA, "kernel does not fit on an SM");
+    *out = sms * per_sm;
+    return PYSP_OK;
+}
+
 int pysp_develop(const pysp_develop_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DevelopPlan plan;
@@ -148,24 +314,53 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
     if (rc) return rc;
     rc = ensure_device();
     if (rc) return rc;
+    const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
     {
-        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              SelectTile<K1_TW, K1_TH>::SMEM_BYTES);
-        cudaError_t e2 = cudaFuncSetAttribute(median_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              MedianTile<K2_TW, K2_TH>::SMEM_BYTES);
+        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        cudaError_t e2 = cudaFuncSetAttribute(median_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
         if (e1 != cudaSuccess || e2 != cudaSuccess)
             return fail(PYSP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
-    {
-        TimedLaunch t(0, stream);
-        ahd_select_kernel<<<plan.select_tiles, K1_THREADS, SelectTile<K1_TW, K1_TH>::SMEM_BYTES, stream>>>(plan.select);
-    }
-    rc = check_launch("ahd_select_kernel");
+    int grid1 = 0, grid2 = 0;
+    rc = resident_ctas((const void*)ahd_select_kernel, K1_THREADS, smem1, &grid1);
     if (rc) return rc;
+    {
+        CUtensorMap in_map;
+        memset(&in_map, 0, sizeof(in_map));
+        OutMaps om;
+        if (plan.select.tma_in) {
+            rc = make_map(&in_map, plan.select.in, SelectTile<K1_TW, K1_TH>::BOXW, SelectTile<K1_TW, K1_TH>::BOXH);
+            if (rc) return rc;
+        }
+        rc = make_out_maps(&om, plan.select.st, K1_TW, K1_TH);
+        if (rc) return rc;
+        const int grid = plan.select.n_tiles < grid1 ? plan.select.n_tiles : grid1;
+        {
+            TimedLaunch t(0, stream);
+            ahd_select_kernel<<<grid, K1_THREADS, smem1, stream>>>(plan.select, in_map, om);
+        }
+        rc = check_launch("ahd_select_kernel");
+        if (rc) return rc;
+    }
+    if (plan.n_stages > 0) {
+        rc = resident_ctas((const void*)median_stage_kernel, K2_THREADS, smem2, &grid2);
+        if (rc) return rc;
+    }
     for (int s = 0; s < plan.n_stages; ++s) {
+        const MedianParams& mp = plan.median[s];
+        OutMaps im, om;
+        memset(&im, 0, sizeof(im));
+        if (mp.tma_in)
+            for (int k = 0; k < 3; ++k) {
+                rc = make_map(&im.m[k], mp.in[k], MedianTile<K2_TW, K2_TH>::AW, MedianTile<K2_TW, K2_TH>::AH);
+                if (rc) return rc;
+            }
+        rc = make_out_maps(&om, mp.st, K2_TW, K2_TH);
+        if (rc) return rc;
+        const int grid = mp.n_tiles < grid2 ? mp.n_tiles : grid2;
         {
             TimedLaunch t(1, stream);
-            median_stage_kernel<<<plan.median_tiles[s], K2_THREADS, MedianTile<K2_TW, K2_TH>::SMEM_BYTES, stream>>>(plan.median[s]);
+            median_stage_kernel<<<grid, K2_THREADS, smem2, stream>>>(mp, im, om);
         }
         rc = check_launch("median_stage_kernel");
         if (rc) return rc;

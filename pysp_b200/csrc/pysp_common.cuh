@@ -60,37 +60,51 @@ struct ColorParams {
     int gamma;           // apply lin_srgb_to_srgb in the epilogue (colorize/transform.py:89-99)
 };
 
-struct SelectParams {    // K1: mosaic -> selected camera RGB (or final output when no median stage)
+struct View2D {          // plain description of a 2-D tensor (rows x cols elements), see tma.cuh
+    void* base;
+    long long pitch;     // bytes
+    int rows, cols;
+    int elem;            // bytes per element
+};
+
+// Output of a kernel of the chain: either the final image (interleaved RGB, stored orientation, clipped to the
+// rows of the band) or the scratch handed to the next median stage: three float planes r-g, b-g, g in logical
+// orientation (debayer/ahd.py:153-154 needs exactly these), so that the next stage loads them by TMA as is.
+enum OutMode { OUT_FINAL = 0, OUT_PLANES = 1 };
+
+struct StoreParams {
+    int mode;            // OutMode
+    int kind;            // OutKind (final only)
+    View2D img;          // final: [band rows][3*W] of f32/f16; row 0 = first stored row of the band
+    int img_row0;        // stored row number of img row 0
+    View2D plane[3];     // planes: [rows][W] f32, row 0 = logical row plane_row0
+    int plane_row0;
+    int tma;             // 1: the views are also described by the tensor maps passed to the kernel
+};
+
+struct SelectParams {    // K1: mosaic -> selected camera RGB
     FrameGeom g;
     ColorParams c;
     int in_kind;
-    const void* in;      // stored orientation; row `in_row0` is the first row present
-    long long in_pitch;  // bytes
-    int in_row0, in_row1;
+    View2D in;           // stored orientation; row 0 = stored row in_row0
+    int in_row0;
+    int tma_in;
     float black[4], white[4];   // by stored-mosaic position TL,TR,BL,BR (normalization.py:20-23)
     const uint2* lut;    // 33^3 nodes of {L,a,b,0} int16 (device)
-    int out_kind;
-    void* out;           // [rows][W][3]; row `out_row0` (orientation of the store, see store_flip) is the first row
-    long long out_pitch;
-    int out_row0;
-    int store_flip;      // 1: write in stored orientation (image.py:181), 0: logical orientation (scratch)
+    StoreParams st;
     int y_begin, y_end;  // logical rows to produce (even)
-    int tiles_x;
+    int tiles_x, n_tiles;
 };
 
-struct MedianParams {    // K2: one postprocess stage (debayer/ahd.py:148-161) on camera RGB
+struct MedianParams {    // K2: one postprocess stage (debayer/ahd.py:148-161)
     FrameGeom g;
     ColorParams c;
-    const float* in;     // [rows][W][3] logical orientation, row in_row0 first
-    long long in_pitch;
-    int in_row0, in_row1;
-    int out_kind;
-    void* out;
-    long long out_pitch;
-    int out_row0;
-    int store_flip;
+    View2D in[3];        // r-g, b-g, g planes, logical orientation, row 0 = logical row in_row0
+    int in_row0;
+    int tma_in;
+    StoreParams st;
     int y_begin, y_end;
-    int tiles_x;
+    int tiles_x, n_tiles;
 };
 
 // ---- border index maps -----------------------------------------------------------------------------

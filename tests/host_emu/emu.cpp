@@ -2,10 +2,12 @@
 //
 // The CUDA tile functions are written as barrier-separated phases whose work items are independent, so
 // the very same source compiles for the host (PYSP_HOST_EMU): a phase runs its items serially, a barrier
-// is a no-op.  This lets tests/test_tile_logic.py diff the exact kernel logic (tiling, halos, the six
-// border rules, band seams, flips) against the oracle in a container without a GPU.  It is NOT a CPU
-// fallback: it is never built into libpysp_b200.so, never imported by the pysp_b200 package, and its
-// entry point takes HOST pointers.  Build: tests/host_emu/build.sh (g++ -ffp-contract=off).
+// is a no-op.  The TMA box transfers are replaced by `box_load_generic` / `store_tile_generic`, which the
+// device build also uses when a tensor cannot be described by a tensor map and which have the TMA's
+// semantics (zero fill on load, clipping on store).  This lets tests/test_tile_logic.py diff the exact kernel
+// logic (tiling, halos, the six border rules, band seams, flips) against the oracle in a container without a
+// GPU.  It is NOT a CPU fallback: it is never built into libpysp_b200.so, never imported by the pysp_b200
+// package, and its entry point takes HOST pointers.  Build: tests/host_emu/build.sh (g++ -ffp-contract=off).
 #define PYSP_HOST_EMU 1
 #include <stdlib.h>
 #include <vector>
@@ -22,47 +24,61 @@ static char g_err[512];
 
 extern "C" const char* emu_last_error(void) { return g_err; }
 
-extern "C" int emu_develop(const pysp_develop_args* a, int tw1, int th1) {
-    // tile sizes are compile-time in the kernels; the emulation instantiates the product's (60x28) and a
-    // small one (12x8) that puts many tile seams and partial tiles into small test frames
-    DevelopPlan plan;
-    int rc = plan_develop(a, tw1, th1, tw1, th1, &plan, g_err, sizeof(g_err));
-    if (rc) return rc;
-    std::vector<float> smem(64 * 1024);
-    auto run_select = [&](auto tile_fn_edge, auto tile_fn_int, int TW, int TH) {
+template <int TW, int TH>
+static void run_chain(const DevelopPlan& plan) {
+    typedef SelectTile<TW, TH> LS;
+    typedef MedianTile<TW, TH> LM;
+    std::vector<float> buf((LS::SMEM_BYTES > LM::SMEM_BYTES ? LS::SMEM_BYTES : LM::SMEM_BYTES) / 4 + 64);
+    char* smem = (char*)buf.data();
+    auto poison = [&]() { for (size_t i = 0; i < buf.size(); ++i) buf[i] = __builtin_nanf(""); };
+    {
         const SelectParams& p = plan.select;
-        for (int t = 0; t < plan.select_tiles; ++t) {
+        for (int t = 0; t < p.n_tiles; ++t) {
             int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-            int x0 = tx * TW, y0 = p.y_begin + ty * TH;
-            bool edge = x0 < 6 || y0 < 6 || x0 + TW + 6 > p.g.W || y0 + TH + 6 > p.g.H || y0 + TH > p.y_end;
-            for (size_t i = 0; i < smem.size(); ++i) smem[i] = __builtin_nanf("");   // poison
-            if (edge) tile_fn_edge(p, smem.data(), tx, ty); else tile_fn_int(p, smem.data(), tx, ty);
-        }
-    };
-    auto run_median = [&](auto tile_fn_edge, auto tile_fn_int, int TW, int TH) {
-        for (int s = 0; s < plan.n_stages; ++s) {
-            const MedianParams& p = plan.median[s];
-            for (int t = 0; t < plan.median_tiles[s]; ++t) {
-                int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-                int x0 = tx * TW, y0 = p.y_begin + ty * TH;
-                bool edge = x0 < 4 || y0 < 4 || x0 + TW + 4 > p.g.W || y0 + TH + 4 > p.g.H || y0 + TH > p.y_end;
-                for (size_t i = 0; i < smem.size(); ++i) smem[i] = __builtin_nanf("");
-                if (edge) tile_fn_edge(p, smem.data(), tx, ty); else tile_fn_int(p, smem.data(), tx, ty);
+            poison();
+            int bx, by;
+            select_input_box<TW, TH>(p, tx, ty, &bx, &by);
+            box_load_generic(smem + LS::OFF_STAGE, p.in, bx, by, LS::BOXW, LS::BOXH);
+            if (select_tile_is_edge<TW, TH>(p, tx, ty)) {
+                select_phase0<TW, TH, true>(p, smem, tx, ty);
+                select_phases<TW, TH, true>(p, smem, tx, ty, []() {});
+            } else {
+                select_phase0<TW, TH, false>(p, smem, tx, ty);
+                select_phases<TW, TH, false>(p, smem, tx, ty, []() {});
             }
+            store_tile_generic<TW, TH>((const float*)(smem + LS::OFF_OUT), p.st, p.g, tx * TW, p.y_begin + ty * TH);
         }
-    };
-    if (tw1 == 60 && th1 == 28) {
-        run_select([](const SelectParams& p, float* s, int x, int y) { select_tile<60, 28, true>(p, s, x, y); },
-                   [](const SelectParams& p, float* s, int x, int y) { select_tile<60, 28, false>(p, s, x, y); }, 60, 28);
-        run_median([](const MedianParams& p, float* s, int x, int y) { median_tile<60, 28, true>(p, s, x, y); },
-                   [](const MedianParams& p, float* s, int x, int y) { median_tile<60, 28, false>(p, s, x, y); }, 60, 28);
-    } else if (tw1 == 12 && th1 == 8) {
-        run_select([](const SelectParams& p, float* s, int x, int y) { select_tile<12, 8, true>(p, s, x, y); },
-                   [](const SelectParams& p, float* s, int x, int y) { select_tile<12, 8, false>(p, s, x, y); }, 12, 8);
-        run_median([](const MedianParams& p, float* s, int x, int y) { median_tile<12, 8, true>(p, s, x, y); },
-                   [](const MedianParams& p, float* s, int x, int y) { median_tile<12, 8, false>(p, s, x, y); }, 12, 8);
-    } else {
-        snprintf(g_err, sizeof(g_err), "emu_develop: tile %dx%d not instantiated", tw1, th1);
+    }
+    for (int s = 0; s < plan.n_stages; ++s) {
+        const MedianParams& p = plan.median[s];
+        for (int t = 0; t < p.n_tiles; ++t) {
+            int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            poison();
+            const int bx = tx * TW - 4, by = p.y_begin + ty * TH - 4 - p.in_row0;
+            for (int k = 0; k < 3; ++k) box_load_generic(smem + LM::OFF_IN + k * LM::PLANE_BYTES, p.in[k], bx, by, LM::AW, LM::AH);
+            if (median_tile_is_edge<TW, TH>(p, tx, ty)) {
+                median_fix_border<TW, TH>(p, smem, tx, ty);
+                median_phase_b<TW, TH, true>(p, smem, tx, ty);
+                median_phase_c<TW, TH, true>(p, smem, tx, ty);
+            } else {
+                median_phase_b<TW, TH, false>(p, smem, tx, ty);
+                median_phase_c<TW, TH, false>(p, smem, tx, ty);
+            }
+            store_tile_generic<TW, TH>((const float*)(smem + LM::OFF_OUT), p.st, p.g, tx * TW, p.y_begin + ty * TH);
+        }
+    }
+}
+
+extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
+    // tile sizes are compile-time in the kernels; the emulation instantiates the product's (60x28) and a small
+    // one (12x8) that puts many tile seams and partial tiles into small test frames
+    DevelopPlan plan;
+    int rc = plan_develop(a, tw, th, tw, th, &plan, g_err, sizeof(g_err));
+    if (rc) return rc;
+    if (tw == 60 && th == 28) run_chain<60, 28>(plan);
+    else if (tw == 12 && th == 8) run_chain<12, 8>(plan);
+    else {
+        snprintf(g_err, sizeof(g_err), "emu_develop: tile %dx%d not instantiated", tw, th);
         return PYSP_ERR_INVALID;
     }
     return PYSP_OK;
