@@ -27,8 +27,11 @@ namespace pysp {
 template <int TW_, int TH_>
 struct SelectTile {
     static constexpr int TW = TW_, TH = TH_;
-    static constexpr int BOXW = TW + 12, BOXH = TH + 12;           // raw input box (tile + 6)
-    static constexpr int QW = BOXW / 2, QH = BOXH / 2;             // quarter planes incl. 3-quad halo
+    // Raw input box: the stencil needs tile + 6 px; horizontally the box starts 8 px left of the tile because a
+    // TMA tile load needs its inner coordinate to be a multiple of 16 bytes (8 u16 / 4 f32; TW % 8 == 0).
+    static constexpr int HX = 8, HY = 6;
+    static constexpr int BOXW = TW + 2 * HX, BOXH = TH + 2 * HY;
+    static constexpr int QW = BOXW / 2, QH = BOXH / 2;             // quarter planes incl. the halo quads
     static constexpr int QN = QW * QH;
     static constexpr int LW = TW + 4, LH = TH + 4;                 // Lab region (tile + 2)
     static constexpr int CW = TW + 2, CH = TH + 2;                 // count region (tile + 1)
@@ -45,7 +48,7 @@ struct SelectTile {
     static constexpr int SMEM_BYTES = align128(OFF_CAND + 4 * TH * TW * 4);
     static constexpr int OFF_OUT = OFF_LABL;       // [3][TH][TW] f32 output tile: aliases Lab (dead after phase 3)
     static constexpr int OFF_CNT = OFF_Q + P_DHR * QN * 4;   // [CH][CW] u8: aliases the D planes (dead after phase 2)
-    static_assert(TW % 4 == 0 && TH % 2 == 0, "tile must be quad aligned (and 16-byte rows)");
+    static_assert(TW % 8 == 0 && TH % 2 == 0, "tile must be quad aligned and start on 16-byte columns");
     static_assert(3 * ((TH * TW * 4 + 127) / 128 * 128) <= 4 * LH * LW * 4, "output tile must fit in the Lab region");
     static_assert(CH * CW <= 4 * QN * 4, "count plane must fit in the D planes");
 };
@@ -58,7 +61,7 @@ struct OutPlane { static constexpr int FLOATS = (TH * TW * 4 + 127) / 128 * 32; 
 template <int TW, int TH>
 PYSP_HD void select_input_box(const SelectParams& p, int tile_x, int tile_y, int* bx, int* by) {
     typedef SelectTile<TW, TH> L;
-    const int x0 = tile_x * TW - 6, y0 = p.y_begin + tile_y * TH - 6;          // logical
+    const int x0 = tile_x * TW - L::HX, y0 = p.y_begin + tile_y * TH - L::HY;  // logical
     *bx = p.g.flip_x ? p.g.W - (x0 + L::BOXW) : x0;
     *by = (p.g.flip_y ? p.g.H - (y0 + L::BOXH) : y0) - p.in_row0;
 }
@@ -194,7 +197,7 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
     typedef SelectTile<TW, TH> L;
     constexpr int QW = L::QW, QN = L::QN;
     const int H = p.g.H, W = p.g.W;
-    const int bx0 = tile_x * TW - 6, by0 = p.y_begin + tile_y * TH - 6;       // logical origin of the box
+    const int bx0 = tile_x * TW - L::HX, by0 = p.y_begin + tile_y * TH - L::HY;   // logical origin of the box
     float* Q = (float*)(smem + L::OFF_Q);
     const void* stage = smem + L::OFF_STAGE;
     PYSP_ITEMS(it, QN) {
@@ -237,7 +240,8 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     const int H = p.g.H, W = p.g.W;
     const int hq = H >> 1, wq = W >> 1;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;     // logical origin of the output tile (even)
-    const int qx0 = (x0 >> 1) - 3, qy0 = (y0 >> 1) - 3;           // quarter-plane origin
+    constexpr int JX = L::HX / 2, IY = L::HY / 2;                 // local quarter index of the tile's first quad
+    const int qx0 = (x0 >> 1) - JX, qy0 = (y0 >> 1) - IY;         // quarter-plane origin
     float* Q = (float*)(smem + L::OFF_Q);
     float* labL = (float*)(smem + L::OFF_LABL);
     uint32_t* labAB = (uint32_t*)(smem + L::OFF_LABAB);
@@ -247,10 +251,10 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
 
     // ---------------- phase 1: directional greens and colour differences at R/B sites ---------------------
     {
-        constexpr int GW = QW - 2, GH = QH - 2;        // quads with a 2-quad halo
+        constexpr int GW = TW / 2 + 4, GH = TH / 2 + 4;   // tile quads with a 2-quad halo
         PYSP_ITEMS(it, GW * GH) {
             int gy = it / GW, gx = it - gy * GW;
-            int i = gy + 1, j = gx + 1;                // local quarter index
+            int i = gy + IY - 2, j = gx + JX - 2;      // local quarter index
             if (EDGE) {
                 int fi = qy0 + i, fj = qx0 + j;
                 if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue;
@@ -276,7 +280,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
         constexpr int PW = L::LW / 2, PH = L::LH / 2;  // quads of the Lab region (1-quad halo)
         PYSP_ITEMS(it, PW * PH) {
             int py = it / PW, px = it - py * PW;
-            int i = py + 2, j = px + 2;                // local quarter index
+            int i = py + IY - 1, j = px + JX - 1;      // local quarter index
             int fi = qy0 + i, fj = qx0 + j;            // frame quarter index
             if (EDGE) { if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue; }
             // local quarter row/col of the 3 neighbours under quarter-grid REFLECT_101
@@ -458,7 +462,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                     int c = cnt[wy[a] * L::CW + wx[b]];
                     sh[a][b] = c & 15; sv[a][b] = c >> 4;
                 }
-            int qi = (oy + 3) * QW + ox + 3;
+            int qi = (oy + IY) * QW + ox + JX;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int a = k >> 1, b = k & 1;

@@ -34,8 +34,12 @@ static inline int64_t develop_scratch_bytes(int32_t width, int32_t rows, int32_t
     return stages >= 2 ? 2 * one : one;
 }
 
-static inline bool tma_ok(const View2D& v) {
-    return ((uintptr_t)v.base % 16) == 0 && (v.pitch % 16) == 0 && v.rows > 0 && v.cols > 0;
+// A view can be moved by TMA when its base and pitch are 16-byte aligned.  Box origins must also land on
+// 16-byte columns: tiles start on such columns by construction, a horizontally flipped frame additionally
+// needs a row length that is a multiple of 16 bytes (`row_bytes`).
+static inline bool tma_ok(const View2D& v, bool flipped_x = false, long long row_bytes = 0) {
+    return ((uintptr_t)v.base % 16) == 0 && (v.pitch % 16) == 0 && v.rows > 0 && v.cols > 0 &&
+           (!flipped_x || row_bytes % 16 == 0);
 }
 
 static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int tw2, int th2, DevelopPlan* plan,
@@ -103,7 +107,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         st.img.base = (char*)a->out + (int64_t)(rb - a->out_row0) * a->out_pitch_bytes;
         st.img.pitch = a->out_pitch_bytes; st.img.rows = re - rb; st.img.cols = 3 * W; st.img.elem = (int)osz;
         st.img_row0 = rb;
-        st.tma = a->out_kind != PYSP_OUT_LIN_F16 && tma_ok(st.img);
+        st.tma = a->out_kind != PYSP_OUT_LIN_F16 && tma_ok(st.img, flip_x != 0, (long long)W * 12);
     };
     auto plane_store = [&](StoreParams& st, int buf, int row0, int rows) {
         st.mode = OUT_PLANES; st.kind = OUT_CAM_F32;
@@ -122,7 +126,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     sp.in_kind = a->in_kind;
     sp.in.base = (void*)a->in; sp.in.pitch = a->in_pitch_bytes; sp.in.rows = a->in_rows; sp.in.cols = W; sp.in.elem = (int)esz;
     sp.in_row0 = a->in_row0;
-    sp.tma_in = tma_ok(sp.in);
+    sp.tma_in = tma_ok(sp.in, flip_x != 0, (long long)W * esz);
     const int perm[4] = {0, 1, 3, 2};          // [TL,TR,BR,BL] -> index (sy&1)*2+(sx&1)
     for (int i = 0; i < 4; ++i) { sp.black[perm[i]] = a->black[i]; sp.white[perm[i]] = a->white[i]; }
     sp.lut = (const uint2*)a->lab_lut;

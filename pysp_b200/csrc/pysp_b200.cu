@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -17,7 +18,7 @@
 
 namespace pysp {
 
-constexpr int K1_TW = 60, K1_TH = 28, K1_THREADS = 256;
+constexpr int K1_TW = 56, K1_TH = 28, K1_THREADS = 256;
 constexpr int K2_TW = 60, K2_TH = 28, K2_THREADS = 256;
 
 struct OutMaps { CUtensorMap m[3]; };     // final image: m[0]; planes: m[0..2]
@@ -314,6 +315,11 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
     if (rc) return rc;
     rc = ensure_device();
     if (rc) return rc;
+    if (const char* e = getenv("PYSP_DISABLE_TMA")) {     // test hook: bit 0 = loads, bit 1 = stores use the generic path
+        const int bits = atoi(e);
+        if (bits & 1) { plan.select.tma_in = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].tma_in = 0; }
+        if (bits & 2) { plan.select.st.tma = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].st.tma = 0; }
+    }
     const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
     {
         cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);

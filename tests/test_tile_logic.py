@@ -44,7 +44,7 @@ def packed_lut():
 LUT = packed_lut()
 
 
-def emu_develop(lib, src, stages, pattern="RGGB", tile=(12, 8), black=syn.BLACK, white=syn.WHITE,
+def emu_develop(lib, src, stages, pattern="RGGB", tile=(16, 8), black=syn.BLACK, white=syn.WHITE,
                 out_kind=_capi.OUT_LIN_F32, band=None, hdr=False, held=None):
     """src: uint16 counts or float32 sensor; `held` = (row0, rows) keeps only that slice of the frame."""
     H, W = src.shape
@@ -68,7 +68,7 @@ def emu_develop(lib, src, stages, pattern="RGGB", tile=(12, 8), black=syn.BLACK,
 def test_frames(emu, shape, stages):
     raw = syn.scene(shape[0], shape[1], 3) if shape[0] > 10 else syn.random_mosaic(shape[0], shape[1], 3)
     lin, cam = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages)
-    for tile in ((12, 8), (60, 28)):
+    for tile in ((16, 8), (56, 28)):
         assert_bit_equal(emu_develop(emu, raw, stages, tile=tile), lin, "lin %s" % (tile,))
         assert_bit_equal(emu_develop(emu, raw, stages, tile=tile, out_kind=_capi.OUT_CAM_F32), cam, "cam %s" % (tile,))
 
