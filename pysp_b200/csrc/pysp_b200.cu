@@ -27,10 +27,12 @@ struct OutMaps { CUtensorMap m[3]; };     // final image: m[0]; planes: m[0..2]
 template <int TW, int TH>
 __device__ __forceinline__ void store_tile(const float* out, const StoreParams& st, const FrameGeom& g, const OutMaps& maps,
                                            int x0, int y0) {
-    if (st.tma) {
+    int bx, by;
+    tile_output_box<TW, TH>(st, g, x0, y0, &bx, &by);
+    // A TMA store clips a box that overshoots the tensor on the high side, but a negative origin is illegal
+    // (measured on B200, tools/probe/tma_store_probe.cu): partial tiles of flipped frames take the generic store.
+    if (st.tma && bx >= 0 && by >= 0) {
         if (threadIdx.x == 0) {
-            int bx, by;
-            tile_output_box<TW, TH>(st, g, x0, y0, &bx, &by);
             if (st.mode == OUT_FINAL) {
                 tma_store_2d(out, &maps.m[0], bx, by);
             } else {

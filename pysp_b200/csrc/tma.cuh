@@ -1,7 +1,10 @@
 // 2-D box transfers between global memory and a dense shared-memory tile.
 //
 // Device: TMA (cp.async.bulk.tensor.2d) with an mbarrier for loads and bulk-group completion for stores;
-// out-of-range box elements are zero-filled on load and dropped on store by the hardware.  When a tensor
+// out-of-range box elements are zero-filled on load and dropped on store by the hardware.  Constraints measured
+// on B200 (tools/probe/): the box origin's inner coordinate must be a multiple of 16 bytes for loads and stores
+// (else "illegal instruction"); loads accept negative origins, stores do not (overshoot on the high side is
+// fine for both).  Shared-memory tiles are 128-byte aligned, base/pitch of the tensor 16-byte aligned.  When a tensor
 // cannot be described by a tensor map (base not 16-byte aligned, pitch not a multiple of 16 bytes) the
 // same transfer is done with ordinary loads/stores by `box_load_generic` / `box_store_generic`, which have
 // identical semantics; the host emulation (tests/host_emu) uses those too.
