@@ -291,7 +291,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 cj[d] = EDGE ? reflect101(fj + d - 1, wq) - qx0 : j + d - 1;
             }
             const bool inner = py >= 1 && py <= TH / 2 && px >= 1 && px <= TW / 2;
-#pragma unroll
+#pragma unroll 1                                       // one copy of the body: it has to stay instruction-cache resident
             for (int dir = 0; dir < 2; ++dir) {
                 const float* GR = Q + (dir ? L::P_GVR : L::P_GHR) * QN;
                 const float* GB = Q + (dir ? L::P_GVB : L::P_GHB) * QN;

@@ -12,6 +12,7 @@
 #include "pysp_common.cuh"
 #include "ahd_select.cuh"   // stage_pixel / store_tile_generic / tile_output_box
 #include "tma.cuh"
+#include "median_block.cuh"
 
 namespace pysp {
 
@@ -83,7 +84,8 @@ PYSP_D void median_fix_border(const MedianParams& p, char* __restrict__ smem, in
     }
 }
 
-// phase B: r', b' and the second difference planes on the tile + 2 px
+// phase B: r', b' and the second difference planes on the tile + 2 px.  One work item = a 2x2 block of pixels whose
+// four 5x5 windows share a 6x6 neighbourhood (median_block.cuh: 89 min/max ops per median instead of 180).
 template <int TW, int TH, bool EDGE>
 PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
     typedef MedianTile<TW, TH> L;
@@ -94,26 +96,35 @@ PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int t
     const float* G = (const float*)(smem + L::OFF_IN + 2 * L::PLANE_BYTES);
     float* ER = (float*)(smem + L::OFF_ER); float* EB = (float*)(smem + L::OFF_EB);
     float* RP = (float*)(smem + L::OFF_RP); float* BP = (float*)(smem + L::OFF_BP);
-    PYSP_ITEMS(it, L::BW * L::BH) {
-        int ly = it / L::BW, lx = it - ly * L::BW;
+    constexpr int NBX = L::BW / 2, NBY = L::BH / 2;
+    PYSP_ITEMS(it, NBX * NBY) {
+        int by = it / NBX, bx = it - by * NBX;
+        int ly = 2 * by, lx = 2 * bx;                       // region-B coords of the block's top-left pixel
         int y = y0 - 2 + ly, x = x0 - 2 + lx;
-        if (EDGE) { if (y < 0 || y >= H || x < 0 || x >= W) continue; }
-        // the input planes hold the REPLICATE extension, so the window around an in-frame pixel is final
-        float wr[25], wb[25];
-        int c = (ly + 2) * L::AW + lx + 2;
+        if (EDGE) { if (y < 0 || y >= H || x < 0 || x >= W) continue; }     // even origin, even frame: all in or all out
+        // the input planes hold the REPLICATE extension, so the windows of in-frame pixels are final
+        float w[6][6], mr[4], mb[4];
+        const int c = ly * L::AW + lx;                      // input-plane index of window cell (0,0) = pixel (y-2, x-2)
 #pragma unroll
-        for (int u = 0; u < 5; ++u)
+        for (int u = 0; u < 6; ++u)
 #pragma unroll
-            for (int v = 0; v < 5; ++v) {
-                int o = c + (u - 2) * L::AW + (v - 2);
-                wr[u * 5 + v] = DR[o]; wb[u * 5 + v] = DB[o];
-            }
-        float g = G[c];
-        float r1 = median25(wr) + g;
-        float b1 = median25(wb) + g;
-        ER[it] = g - r1; EB[it] = g - b1;
-        int ty = ly - 2, tx = lx - 2;
-        if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { RP[ty * TW + tx] = r1; BP[ty * TW + tx] = b1; }
+            for (int v = 0; v < 6; ++v) w[u][v] = DR[c + u * L::AW + v];
+        median25_block2x2(w, mr);
+#pragma unroll
+        for (int u = 0; u < 6; ++u)
+#pragma unroll
+            for (int v = 0; v < 6; ++v) w[u][v] = DB[c + u * L::AW + v];
+        median25_block2x2(w, mb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dy = k >> 1, dx = k & 1;
+            float g = G[c + (2 + dy) * L::AW + 2 + dx];
+            float r1 = mr[k] + g, b1 = mb[k] + g;
+            int o = (ly + dy) * L::BW + lx + dx;
+            ER[o] = g - r1; EB[o] = g - b1;
+            int ty = ly + dy - 2, tx = lx + dx - 2;
+            if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { RP[ty * TW + tx] = r1; BP[ty * TW + tx] = b1; }
+        }
     }
 }
 
@@ -123,29 +134,42 @@ PYSP_D void median_phase_c(const MedianParams& p, char* __restrict__ smem, int t
     typedef MedianTile<TW, TH> L;
     const int H = p.g.H, W = p.g.W;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
-    const float* G = (const float*)(smem + L::OFF_IN + 2 * L::PLANE_BYTES);
     const float* ER = (const float*)(smem + L::OFF_ER); const float* EB = (const float*)(smem + L::OFF_EB);
     const float* RP = (const float*)(smem + L::OFF_RP); const float* BP = (const float*)(smem + L::OFF_BP);
     float* out = (float*)(smem + L::OFF_OUT);
-    (void)G;
-    PYSP_ITEMS(it, TW * TH) {
-        int ty = it / TW, tx = it - ty * TW;
+    constexpr int NBX = TW / 2, NBY = TH / 2;
+    PYSP_ITEMS(it, NBX * NBY) {
+        int by = it / NBX, bx = it - by * NBX;
+        int ty = 2 * by, tx = 2 * bx;
         int y = y0 + ty, x = x0 + tx;
         if (EDGE) { if (y >= H || x >= W) continue; }
-        float wr[25], wb[25];
+        int ry[6], rx[6];                                   // region-B rows/cols of the 6x6 window (REPLICATE at the frame border)
 #pragma unroll
-        for (int u = 0; u < 5; ++u)
+        for (int k = 0; k < 6; ++k) {
+            ry[k] = EDGE ? clampi(y + k - 2, H) - (y0 - 2) : ty + k;
+            rx[k] = EDGE ? clampi(x + k - 2, W) - (x0 - 2) : tx + k;
+        }
+        float w[6][6], mr[4], mb[4];
 #pragma unroll
-            for (int v = 0; v < 5; ++v) {
-                int yy = EDGE ? clampi(y + u - 2, H) - (y0 - 2) : ty + u;
-                int xx = EDGE ? clampi(x + v - 2, W) - (x0 - 2) : tx + v;
-                wr[u * 5 + v] = ER[yy * L::BW + xx]; wb[u * 5 + v] = EB[yy * L::BW + xx];
-            }
-        float r1 = RP[it], b1 = BP[it];
-        Rgb v;
-        v.r = r1; v.b = b1;
-        v.g = (((median25(wr) + median25(wb)) + r1) + b1) / 2.0f;
-        stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty, tx, v);
+        for (int u = 0; u < 6; ++u)
+#pragma unroll
+            for (int v = 0; v < 6; ++v) w[u][v] = ER[ry[u] * L::BW + rx[v]];
+        median25_block2x2(w, mr);
+#pragma unroll
+        for (int u = 0; u < 6; ++u)
+#pragma unroll
+            for (int v = 0; v < 6; ++v) w[u][v] = EB[ry[u] * L::BW + rx[v]];
+        median25_block2x2(w, mb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dy = k >> 1, dx = k & 1;
+            int o = (ty + dy) * TW + tx + dx;
+            float r1 = RP[o], b1 = BP[o];
+            Rgb v;
+            v.r = r1; v.b = b1;
+            v.g = (((mr[k] + mb[k]) + r1) + b1) / 2.0f;
+            stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty + dy, tx + dx, v);
+        }
     }
 }
 

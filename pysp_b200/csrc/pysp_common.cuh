@@ -17,6 +17,7 @@
 #include <string.h>
 #define PYSP_HD inline
 #define PYSP_D inline
+#define PYSP_NOINLINE inline
 #define PYSP_SYNC() ((void)0)
 #define PYSP_ITEMS(var, n) for (int var = 0; var < (n); ++var)
 static inline float pysp_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -26,6 +27,8 @@ template <typename T> static inline T pysp_ldg(const T* p) { return *p; }
 #include <cuda_runtime.h>
 #define PYSP_HD __device__ __forceinline__
 #define PYSP_D __device__ __forceinline__
+// called once per pixel and direction: kept out of line so that the phase bodies fit the instruction cache
+#define PYSP_NOINLINE __device__ __noinline__
 #define PYSP_SYNC() __syncthreads()
 #define PYSP_ITEMS(var, n) for (int var = threadIdx.x; var < (n); var += blockDim.x)
 __device__ __forceinline__ float pysp_as_float(uint32_t u) { return __uint_as_float(u); }
@@ -129,7 +132,7 @@ PYSP_HD float dot3_f64(const double* m, float c0, float c1, float c2) {
 PYSP_HD float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
 // colorize/transform.py:98-99 in float32
-PYSP_HD float srgb_gamma(float v) {
+PYSP_NOINLINE float srgb_gamma(float v) {
     float x = clip01(v);
     return x <= 0.0031308f ? x * 12.92f : (1.055f * powf(x, (float)(1.0 / 2.4))) - 0.055f;
 }
@@ -184,7 +187,7 @@ PYSP_HD float ab_lo(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab & 0xFF
 PYSP_HD float ab_hi(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab >> 16)); }
 
 // debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
-PYSP_HD LabQ metric_lab(const ColorParams& c, const uint2* __restrict__ lut, float r, float g, float b) {
+PYSP_NOINLINE LabQ metric_lab(const ColorParams& c, const uint2* __restrict__ lut, float r, float g, float b) {
     float c0 = r * c.wb[0], c1 = g * c.wb[1], c2 = b * c.wb[2];        // WB applied a 2nd time (ahd.py:46-48)
     float sr = dot3_f64(c.m_metric + 0, c0, c1, c2);
     float sg = dot3_f64(c.m_metric + 3, c0, c1, c2);
