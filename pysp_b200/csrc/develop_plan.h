@@ -129,7 +129,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     sp.tma_in = tma_ok(sp.in, flip_x != 0, (long long)W * esz);
     const int perm[4] = {0, 1, 3, 2};          // [TL,TR,BR,BL] -> index (sy&1)*2+(sx&1)
     for (int i = 0; i < 4; ++i) { sp.black[perm[i]] = a->black[i]; sp.white[perm[i]] = a->white[i]; }
-    sp.lut = (const uint2*)a->lab_lut;
+    sp.lut = (const uint4*)a->lab_lut;
     sp.y_begin = k1b; sp.y_end = k1e;
     sp.tiles_x = (W + tw1 - 1) / tw1;
     sp.n_tiles = sp.tiles_x * ((k1e - k1b + th1 - 1) / th1);

@@ -244,16 +244,22 @@ int64_t pysp_develop_scratch_bytes(int32_t width, int32_t rows, int32_t stages) 
     return develop_scratch_bytes(width, rows, stages);
 }
 
-int64_t pysp_lab_lut_bytes(void) { return 33LL * 33 * 33 * 8; }
+int64_t pysp_lab_lut_bytes(void) { return (int64_t)PYSP_LUT_NR * PYSP_LUT_NG * PYSP_LUT_NB * 16; }
 
 int pysp_lab_lut_pack_host(const int16_t* lut, void* packed) {
     if (!lut || !packed) return fail(PYSP_ERR_INVALID, "pysp_lab_lut_pack_host: null pointer");
     uint32_t* o = (uint32_t*)packed;
-    for (int i = 0; i < 33 * 33 * 33; ++i) {
-        uint32_t L = (uint16_t)lut[3 * i], a = (uint16_t)lut[3 * i + 1], b = (uint16_t)lut[3 * i + 2];
-        o[2 * i] = L | (a << 16);
-        o[2 * i + 1] = b;
-    }
+    auto at = [&](int r, int g, int b, int ch) -> uint32_t {
+        r = r > 32 ? 32 : r; g = g > 32 ? 32 : g; b = b > 32 ? 32 : b;
+        return (uint16_t)lut[((r * 33 + g) * 33 + b) * 3 + ch];
+    };
+    for (int r = 0; r < PYSP_LUT_NR; ++r)
+        for (int g = 0; g < PYSP_LUT_NG; ++g)
+            for (int b = 0; b < PYSP_LUT_NB; ++b) {
+                uint32_t* e = o + (((size_t)r * PYSP_LUT_NG + g) * PYSP_LUT_NB + b) * 4;
+                for (int ch = 0; ch < 3; ++ch) e[ch] = at(r, g, b, ch) | (at(r, g, b + 1, ch) << 16);
+                e[3] = 0;
+            }
     return PYSP_OK;
 }
 

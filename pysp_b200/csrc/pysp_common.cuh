@@ -93,7 +93,7 @@ struct SelectParams {    // K1: mosaic -> selected camera RGB
     int in_row0;
     int tma_in;
     float black[4], white[4];   // by stored-mosaic position TL,TR,BL,BR (normalization.py:20-23)
-    const uint2* lut;    // 33^3 nodes of {L,a,b,0} int16 (device)
+    const uint4* lut;    // paired-node Lab table (device), see lab_lookup
     StoreParams st;
     int y_begin, y_end;  // logical rows to produce (even)
     int tiles_x, n_tiles;
@@ -141,44 +141,63 @@ PYSP_NOINLINE float srgb_gamma(float v) {
 // Returns L as the reference float (v*100/16384) and (a,b) as the raw integers v (a = v/64-128 exactly,
 // so differences and squared distances of the integers are the reference's scaled by exact powers of
 // two; every comparison in the homogeneity count is unchanged).
+//
+// Device table layout (pysp_lab_lut_pack_host): node (ir, ig, ib), ir, ig in 0..33 (index 33 repeats 32 so the
+// upper corner needs no clamp: its weight is zero there), ib in 0..32, is a uint4
+//     { L[ib] | L[ib+1] << 16,  a[ib] | a[ib+1] << 16,  b[ib] | b[ib+1] << 16,  0 }
+// so one 16-byte load brings both blue corners of all three channels and the blue interpolation is a 2-way
+// 16x8-bit dot product (IDP.2A).  The sum of the eight weighted corners is integer arithmetic, hence exact in
+// any association: interpolate along blue, then green, then red.
 struct LabQ { float L; uint32_t ab; };
+#define PYSP_LUT_NR 34
+#define PYSP_LUT_NG 34
+#define PYSP_LUT_NB 33
 
-PYSP_HD int quant14(float v) {
-    // cvRound(clip(v,0,1)*16384): the product is exact, adding 2^23 rounds half-to-even
-    float y = clip01(v) * 16384.0f + 8388608.0f;
-    return (int)(pysp_as_uint(y) & 0x7FFFFFu);
+#if !defined(PYSP_HOST_EMU) && !defined(__CUDACC__)
+struct uint4 { unsigned int x, y, z, w; };
+#endif
+
+PYSP_HD uint32_t quant14(float v) {
+    // cvRound(clip(v,0,1)*16384): the product is exact, adding 2^23 rounds half-to-even (one FMA: exact product)
+#ifdef __CUDA_ARCH__
+    float y = fmaf(__saturatef(v), 16384.0f, 8388608.0f);
+#else
+    float y = fmaf(clip01(v), 16384.0f, 8388608.0f);
+#endif
+    return pysp_as_uint(y) & 0x7FFFFFu;
 }
 
-PYSP_HD LabQ lab_lookup(const uint2* __restrict__ lut, float r, float g, float b) {
-    int cr = quant14(r), cg = quant14(g), cb = quant14(b);
-    int tr = cr >> 9, tg = cg >> 9, tb = cb >> 9;
-    int sr = (cr >> 5) & 15, sg = (cg >> 5) & 15, sb = (cb >> 5) & 15;
-    // upper corner index is clamped: it only matters when its weight is zero (c == 16384)
-    int tr1 = tr < 32 ? tr + 1 : 32, tg1 = tg < 32 ? tg + 1 : 32, tb1 = tb < 32 ? tb + 1 : 32;
-    int accL = 2048, accA = 2048, accB = 2048;
-#define PYSP_CORNER(ir, ig, ib, w)                                                 \
-    {                                                                              \
-        uint2 e = pysp_ldg(lut + ((ir) * 33 + (ig)) * 33 + (ib));                  \
-        int wv = (w);                                                              \
-        accL += (int)(e.x & 0xFFFFu) * wv;                                         \
-        accA += (int)(e.x >> 16) * wv;                                             \
-        accB += (int)(e.y & 0xFFFFu) * wv;                                         \
+PYSP_HD uint32_t dot2_u16_u8(uint32_t pair16, uint32_t w8, uint32_t acc) {
+#ifdef __CUDA_ARCH__
+    return __dp2a_lo(pair16, w8, acc);
+#else
+    return acc + (pair16 & 0xFFFFu) * (w8 & 0xFFu) + (pair16 >> 16) * ((w8 >> 8) & 0xFFu);
+#endif
+}
+
+PYSP_HD LabQ lab_lookup(const uint4* __restrict__ lut, float r, float g, float b) {
+    const uint32_t cr = quant14(r), cg = quant14(g), cb = quant14(b);
+    const uint32_t tr = cr >> 9, tg = cg >> 9, tb = cb >> 9;
+    const uint32_t sr = (cr >> 5) & 15u, sg = (cg >> 5) & 15u, sb = (cb >> 5) & 15u;
+    const uint4* base = lut + (tr * PYSP_LUT_NG + tg) * PYSP_LUT_NB + tb;
+    const uint4 e00 = pysp_ldg(base);
+    const uint4 e01 = pysp_ldg(base + PYSP_LUT_NB);
+    const uint4 e10 = pysp_ldg(base + PYSP_LUT_NG * PYSP_LUT_NB);
+    const uint4 e11 = pysp_ldg(base + PYSP_LUT_NG * PYSP_LUT_NB + PYSP_LUT_NB);
+    const uint32_t wb = (16u - sb) | (sb << 8), wg0 = 16u - sg, wr0 = 16u - sr;
+    uint32_t v[3];
+#define PYSP_CH(k, f)                                                                              \
+    {                                                                                              \
+        uint32_t p00 = dot2_u16_u8(e00.f, wb, 0u), p01 = dot2_u16_u8(e01.f, wb, 0u);               \
+        uint32_t p10 = dot2_u16_u8(e10.f, wb, 0u), p11 = dot2_u16_u8(e11.f, wb, 0u);               \
+        uint32_t q0 = p00 * wg0 + p01 * sg, q1 = p10 * wg0 + p11 * sg;                             \
+        v[k] = (q0 * wr0 + q1 * sr + 2048u) >> 12;                                                 \
     }
-    int wr0 = 16 - sr, wg0 = 16 - sg, wb0 = 16 - sb;
-    int w00 = wr0 * wg0, w01 = wr0 * sg, w10 = sr * wg0, w11 = sr * sg;
-    PYSP_CORNER(tr, tg, tb, w00 * wb0)
-    PYSP_CORNER(tr, tg, tb1, w00 * sb)
-    PYSP_CORNER(tr, tg1, tb, w01 * wb0)
-    PYSP_CORNER(tr, tg1, tb1, w01 * sb)
-    PYSP_CORNER(tr1, tg, tb, w10 * wb0)
-    PYSP_CORNER(tr1, tg, tb1, w10 * sb)
-    PYSP_CORNER(tr1, tg1, tb, w11 * wb0)
-    PYSP_CORNER(tr1, tg1, tb1, w11 * sb)
-#undef PYSP_CORNER
+    PYSP_CH(0, x) PYSP_CH(1, y) PYSP_CH(2, z)
+#undef PYSP_CH
     LabQ q;
-    int vL = accL >> 12, vA = accA >> 12, vB = accB >> 12;     // table values are non-negative
-    q.L = (pysp_as_float(0x4B000000u | (uint32_t)vL) - 8388608.0f) * (100.0f / 16384.0f);
-    q.ab = (uint32_t)vA | ((uint32_t)vB << 16);
+    q.L = (pysp_as_float(0x4B000000u | v[0]) - 8388608.0f) * (100.0f / 16384.0f);
+    q.ab = v[1] | (v[2] << 16);
     return q;
 }
 
@@ -187,7 +206,7 @@ PYSP_HD float ab_lo(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab & 0xFF
 PYSP_HD float ab_hi(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab >> 16)); }
 
 // debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
-PYSP_NOINLINE LabQ metric_lab(const ColorParams& c, const uint2* __restrict__ lut, float r, float g, float b) {
+PYSP_HD LabQ metric_lab(const ColorParams& c, const uint4* __restrict__ lut, float r, float g, float b) {
     float c0 = r * c.wb[0], c1 = g * c.wb[1], c2 = b * c.wb[2];        // WB applied a 2nd time (ahd.py:46-48)
     float sr = dot3_f64(c.m_metric + 0, c0, c1, c2);
     float sg = dot3_f64(c.m_metric + 3, c0, c1, c2);

@@ -12,7 +12,7 @@
 #include <stdlib.h>
 #include <vector>
 
-struct uint2 { unsigned int x, y; };
+struct uint4 { unsigned int x, y, z, w; };
 
 #include "../../pysp_b200/csrc/ahd_select.cuh"
 #include "../../pysp_b200/csrc/median_stage.cuh"

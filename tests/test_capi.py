@@ -84,13 +84,18 @@ def test_helpers(lib):
     assert lib.pysp_develop_scratch_bytes(100, 50, 0) == 0
     assert lib.pysp_develop_scratch_bytes(100, 50, 1) == (50 + 8) * 100 * 12
     assert lib.pysp_develop_scratch_bytes(100, 50, 3) == 2 * (50 + 24) * 100 * 12
-    assert lib.pysp_lab_lut_bytes() == 33 ** 3 * 8
-    lut = np.arange(33 ** 3 * 3, dtype=np.int64).reshape(-1, 3) % 16384
+    assert lib.pysp_lab_lut_bytes() == 34 * 34 * 33 * 16
+    lut = (np.arange(33 ** 3 * 3, dtype=np.int64).reshape(33, 33, 33, 3) * 7) % 16384
     lut16 = np.ascontiguousarray(lut.astype(np.int16))
-    packed = np.zeros(33 ** 3 * 2, dtype=np.uint32)
+    packed = np.zeros(34 * 34 * 33 * 4, dtype=np.uint32)
     assert lib.pysp_lab_lut_pack_host(lut16.ctypes.data, packed.ctypes.data) == 0
-    assert np.array_equal(packed[0::2] & 0xFFFF, lut[:, 0]) and np.array_equal(packed[0::2] >> 16, lut[:, 1])
-    assert np.array_equal(packed[1::2], lut[:, 2])
+    p = packed.reshape(34, 34, 33, 4)
+    for ch in range(3):
+        assert np.array_equal(p[:33, :33, :, ch] & 0xFFFF, lut[..., ch])
+        assert np.array_equal(p[:33, :33, :32, ch] >> 16, lut[:, :, 1:, ch])
+        assert np.array_equal(p[:33, :33, 32, ch] >> 16, lut[:, :, 32, ch])
+        assert np.array_equal(p[33, :33, :, ch], p[32, :33, :, ch]) and np.array_equal(p[:, 33, :, ch], p[:, 32, :, ch])
+    assert not p[..., 3].any()
     assert b"sm_100a" in lib.pysp_version()
 
 

@@ -34,10 +34,13 @@ def emu():
 
 
 def packed_lut():
-    l = np.load(os.path.join(ROOT, "pysp_b200", "data", "lab_lut33_i16.npy")).reshape(-1, 3).astype(np.uint16).astype(np.uint32)
-    p = np.zeros((l.shape[0], 2), dtype=np.uint32)
-    p[:, 0] = l[:, 0] | (l[:, 1] << 16)
-    p[:, 1] = l[:, 2]
+    """the device layout of the Lab table, produced by the library's own (host-side) packer"""
+    from pysp_b200 import build
+    build.build()
+    L = _capi.lib()
+    lut = np.ascontiguousarray(np.load(os.path.join(ROOT, "pysp_b200", "data", "lab_lut33_i16.npy")).astype(np.int16))
+    p = np.zeros(int(L.pysp_lab_lut_bytes()), dtype=np.uint8)
+    assert L.pysp_lab_lut_pack_host(lut.ctypes.data, p.ctypes.data) == 0
     return p
 
 
