@@ -192,6 +192,19 @@ PYSP_HD void up_br(const float v[3][3], float o[4]) {
 PYSP_HD float gauss_row(float l, float c, float r) { return (PYSP_GK1 * c) + (PYSP_GK0 * (l + r)); }
 
 // ---- phase 0: staging box -> normalised, white-balanced quarter planes -------------------------------------
+// normalization.py:20-23 on one photosite: clip(raw - black, 0, white) / white.  The IEEE division is replaced,
+// when the host has checked it exhaustively for these levels (all 65536 sensor codes, develop_plan.h), by the
+// reciprocal + two-FMA correction q = t*r; q' = fma(fma(-q, w, t), r, q), which then gives the same float.
+PYSP_HD float normalize_site(const SelectParams& p, uint32_t code, int pos) {
+    float raw = pysp_as_float(0x4B000000u | code) - 8388608.0f;          // exact u16 -> float
+    float t = fminf(fmaxf(raw - p.black[pos], 0.0f), p.white[pos]);
+    if (p.fast_div) {
+        float q = t * p.rwhite[pos];
+        return fmaf(fmaf(-q, p.white[pos], t), p.rwhite[pos], q);
+    }
+    return t / p.white[pos];
+}
+
 template <int TW, int TH, bool EDGE>
 PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
     typedef SelectTile<TW, TH> L;
@@ -200,33 +213,41 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
     const int bx0 = tile_x * TW - L::HX, by0 = p.y_begin + tile_y * TH - L::HY;   // logical origin of the box
     float* Q = (float*)(smem + L::OFF_Q);
     const void* stage = smem + L::OFF_STAGE;
+    const int flipmask = (p.g.flip_y << 1) | p.g.flip_x;      // stored CFA position of logical position k is k ^ flipmask
     PYSP_ITEMS(it, QN) {
         int qy = it / QW, qx = it - qy * QW;
         float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int ly = 2 * qy + (k >> 1), lx = 2 * qx + (k & 1);                // local logical coords in the box
-            int y = by0 + ly, x = bx0 + lx;
-            if (EDGE) {
-                y = phase_clamp(y, H); x = phase_clamp(x, W);
-                ly = y - by0; lx = x - bx0;
-            }
-            int sly = p.g.flip_y ? L::BOXH - 1 - ly : ly, slx = p.g.flip_x ? L::BOXW - 1 - lx : lx;
-            int si = sly * L::BOXW + slx;
-            float s;
+        if (!EDGE) {
+            // the two sites of a mosaic row are adjacent in the staging box (also when mirrored): one 32/64-bit load
+            const int r0 = p.g.flip_y ? L::BOXH - 1 - 2 * qy : 2 * qy, r1 = p.g.flip_y ? r0 - 1 : r0 + 1;
+            const int cp = p.g.flip_x ? QW - 1 - qx : qx;
             if (p.in_kind == IN_U16) {
-                int sy = p.g.flip_y ? H - 1 - y : y, sx = p.g.flip_x ? W - 1 - x : x;   // stored parity picks the level
-                int pos = ((sy & 1) << 1) | (sx & 1);
-                float raw = (float)((const uint16_t*)stage)[si];
-                float t = fminf(fmaxf(raw - p.black[pos], 0.0f), p.white[pos]);
-                s = t / p.white[pos];
+                uint32_t w0 = ((const uint32_t*)stage)[r0 * QW + cp], w1 = ((const uint32_t*)stage)[r1 * QW + cp];
+                if (p.g.flip_x) { w0 = (w0 >> 16) | (w0 << 16); w1 = (w1 >> 16) | (w1 << 16); }
+                v[0] = normalize_site(p, w0 & 0xFFFFu, 0 ^ flipmask);
+                v[1] = normalize_site(p, w0 >> 16, 1 ^ flipmask);
+                v[2] = normalize_site(p, w1 & 0xFFFFu, 2 ^ flipmask);
+                v[3] = normalize_site(p, w1 >> 16, 3 ^ flipmask);
             } else {
-                s = ((const float*)stage)[si];
+                const float* sf = (const float*)stage;
+                float a0 = sf[(r0 * QW + cp) * 2], a1 = sf[(r0 * QW + cp) * 2 + 1];
+                float b0 = sf[(r1 * QW + cp) * 2], b1 = sf[(r1 * QW + cp) * 2 + 1];
+                v[0] = p.g.flip_x ? a1 : a0; v[1] = p.g.flip_x ? a0 : a1;
+                v[2] = p.g.flip_x ? b1 : b0; v[3] = p.g.flip_x ? b0 : b1;
             }
-            v[k] = s * p.c.wb[(k >> 1) + (k & 1)];                          // R:0  G:1  B:2
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // phase-preserving clamp (ahd.py:77-80): the clamped site is always inside the same box
+                int y = phase_clamp(by0 + 2 * qy + (k >> 1), H), x = phase_clamp(bx0 + 2 * qx + (k & 1), W);
+                int ly = y - by0, lx = x - bx0;
+                int si = (p.g.flip_y ? L::BOXH - 1 - ly : ly) * L::BOXW + (p.g.flip_x ? L::BOXW - 1 - lx : lx);
+                v[k] = p.in_kind == IN_U16 ? normalize_site(p, ((const uint16_t*)stage)[si], k ^ flipmask)
+                                           : ((const float*)stage)[si];
+            }
         }
-        Q[L::P_R * QN + it] = v[0]; Q[L::P_G1 * QN + it] = v[1];
-        Q[L::P_G2 * QN + it] = v[2]; Q[L::P_B * QN + it] = v[3];
+        Q[L::P_R * QN + it] = v[0] * p.c.wb[0]; Q[L::P_G1 * QN + it] = v[1] * p.c.wb[1];
+        Q[L::P_G2 * QN + it] = v[2] * p.c.wb[1]; Q[L::P_B * QN + it] = v[3] * p.c.wb[2];
     }
 }
 

@@ -5,7 +5,10 @@
 #pragma once
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "../../include/pysp_b200.h"
 #include "pysp_common.cuh"
@@ -37,6 +40,34 @@ static inline int64_t develop_scratch_bytes(int32_t width, int32_t rows, int32_t
 // A view can be moved by TMA when its base and pitch are 16-byte aligned.  Box origins must also land on
 // 16-byte columns: tiles start on such columns by construction, a horizontally flipped frame additionally
 // needs a row length that is a multiple of 16 bytes (`row_bytes`).
+// normalization.py:20-23 divides clip(raw - black, 0, white) by white.  For 16-bit input there are only 65536 sensor
+// codes per CFA site, so the host checks exhaustively whether q' = fma(fma(-q, w, t), r, q), q = t*r, r = float(1/w)
+// reproduces the IEEE quotient t/w for every code; the kernel then uses that instead of the division sequence.
+// The last verdict is cached (levels rarely change between calls).
+static inline bool fast_division_is_exact(const float black[4], const float white[4]) {
+    static float c_black[4], c_white[4];
+    static int c_valid = 0, c_result = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (c_valid && !memcmp(c_black, black, 16) && !memcmp(c_white, white, 16)) return c_result != 0;
+    bool ok = true;
+    for (int pos = 0; pos < 4 && ok; ++pos) {
+        const float w = white[pos], b = black[pos];
+        if (!(w > 0.0f) || !(w < 1e30f)) { ok = false; break; }
+        const float r = 1.0f / w;
+        for (int code = 0; code < 65536; ++code) {
+            float t = fminf(fmaxf((float)code - b, 0.0f), w);
+            volatile float q = t * r;
+            float fast = fmaf(fmaf(-q, w, t), r, q);
+            volatile float exact = t / w;
+            if (!(fast == exact)) { ok = false; break; }
+        }
+    }
+    memcpy(c_black, black, 16); memcpy(c_white, white, 16);
+    c_valid = 1; c_result = ok ? 1 : 0;
+    return ok;
+}
+
 static inline bool tma_ok(const View2D& v, bool flipped_x = false, long long row_bytes = 0) {
     return ((uintptr_t)v.base % 16) == 0 && (v.pitch % 16) == 0 && v.rows > 0 && v.cols > 0 &&
            (!flipped_x || row_bytes % 16 == 0);
@@ -129,6 +160,10 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     sp.tma_in = tma_ok(sp.in, flip_x != 0, (long long)W * esz);
     const int perm[4] = {0, 1, 3, 2};          // [TL,TR,BR,BL] -> index (sy&1)*2+(sx&1)
     for (int i = 0; i < 4; ++i) { sp.black[perm[i]] = a->black[i]; sp.white[perm[i]] = a->white[i]; }
+    if (a->in_kind == PYSP_IN_U16) {
+        for (int i = 0; i < 4; ++i) sp.rwhite[i] = 1.0f / sp.white[i];
+        sp.fast_div = fast_division_is_exact(sp.black, sp.white) ? 1 : 0;
+    }
     sp.lut = (const uint4*)a->lab_lut;
     sp.y_begin = k1b; sp.y_end = k1e;
     sp.tiles_x = (W + tw1 - 1) / tw1;

@@ -323,10 +323,12 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
     if (rc) return rc;
     rc = ensure_device();
     if (rc) return rc;
-    if (const char* e = getenv("PYSP_DISABLE_TMA")) {     // test hook: bit 0 = loads, bit 1 = stores use the generic path
+    if (const char* e = getenv("PYSP_DISABLE_TMA")) {     // test hook: bit 0 = loads, bit 1 = stores use the generic path,
+                                                          // bit 2 = IEEE division instead of the verified reciprocal form
         const int bits = atoi(e);
         if (bits & 1) { plan.select.tma_in = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].tma_in = 0; }
         if (bits & 2) { plan.select.st.tma = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].st.tma = 0; }
+        if (bits & 4) plan.select.fast_div = 0;
     }
     const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
     {

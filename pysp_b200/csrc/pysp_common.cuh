@@ -93,6 +93,8 @@ struct SelectParams {    // K1: mosaic -> selected camera RGB
     int in_row0;
     int tma_in;
     float black[4], white[4];   // by stored-mosaic position TL,TR,BL,BR (normalization.py:20-23)
+    float rwhite[4];     // float(1/white)
+    int fast_div;        // 1: reciprocal + FMA correction verified equal to IEEE division for these levels
     const uint4* lut;    // paired-node Lab table (device), see lab_lookup
     StoreParams st;
     int y_begin, y_end;  // logical rows to produce (even)

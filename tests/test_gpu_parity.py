@@ -183,6 +183,30 @@ def test_hdr_fuse(eng):
     assert P.fuse_exposures_to_raw([]) is None
 
 
+@pytest.mark.parametrize("mode", ["1", "2", "7"])
+def test_generic_paths(mode):
+    """The non-TMA load/store paths and the IEEE-division path (taken for unaligned tensors / unverified levels)
+    give the same bits; forced here through the library's test hook in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import ahd_spec as sp\n"
+        "from pysp_b200 import engine, synthetic as syn\n"
+        "raw = syn.scene(200, 320, 1)\n"
+        "m = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)\n"
+        "for pat, st in (('RGGB', 2), ('BGGR', 1), ('GBRG', 0)):\n"
+        "    out = engine.develop(engine.to_device(raw), syn.wb_multipliers(), m, stages=st, pattern=pat, black=syn.BLACK, white=syn.WHITE)\n"
+        "    lin, _ = sp.develop(raw, syn.BLACK, syn.WHITE, syn.wb_multipliers(), syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, st, pat)\n"
+        "    assert np.array_equal(out.cpu().numpy().view(np.uint32), lin.view(np.uint32)), pat\n"
+        "print('ok')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYSP_DISABLE_TMA=mode), capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_large_frame_smoke(eng):
     """100 MP frame (config 5): runs, finite, deterministic checksum across two runs."""
     H, W = 8660, 11548
