@@ -129,7 +129,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    os.environ["OMP_NUM_THREADS"] = str(threads)     # torchrun pins it to 1; the CPU arm uses every host thread
     once, kind = cpu_port(CPU_SAMPLE, threads)
     for _ in range(args.warmup):
         once()
@@ -283,6 +283,7 @@ def main():
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
+            os.environ["OMP_NUM_THREADS"] = str(threads)
             once, kind = cpu_port(CPU_SAMPLE, threads)
             once()
             best = min(once() for _ in range(2))
