@@ -1,0 +1,88 @@
+"""N-GPU check (torchrun, NCCL): (1) one large frame over row bands with a halo exchange of raw rows between
+neighbours, (2) HDR brackets owned round-robin, exchanged by rows and fused in list order; both must reproduce the
+single-GPU result bit for bit.  Prints one JSON line from rank 0.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/multi_gpu_check.py
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from pysp_b200 import engine, parallel, synthetic as syn  # noqa: E402
+from pysp_b200.colour import cam_to_rgb_matrix  # noqa: E402
+from pysp_b200.raw_hdr import fusion_constants  # noqa: E402
+from pysp_b200.wb_cct import CameraWhiteBalance  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    wbc = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    wb, m = wbc.get_reciprocal_multipliers(), cam_to_rgb_matrix(wbc.get_matrix())
+    H, W, stages = 8660, 11548, 1                      # BASELINE config 5: one 100 MP frame
+    small = syn.scene(H // 4 + 2, W // 4 + 2, 3)
+    frame = np.tile(small, (4, 4))[:H, :W].copy()
+    kw = dict(wb=wb, cam_to_srgb=m, stages=stages, black=syn.BLACK, white=syn.WHITE)
+    # --- row bands: every rank starts with ONLY its band of the mosaic on its GPU ---
+    b, e = parallel.band_rows(H, world, rank)
+    band = torch.from_numpy(frame[b:e].view(np.int16)).to(dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    out = parallel.develop_band(band, H, stages, lambda held, hb, rows: engine.develop(
+        held, rows=rows, frame_height=H, in_row0=hb, **kw))
+    torch.cuda.synchronize(); dist.barrier()
+    t_band = time.perf_counter() - t0
+    # reference: rank 0 develops the whole frame alone and compares every band
+    checks = [None] * world
+    dist.all_gather_object(checks, (b, e, out.view(torch.int32).to(torch.int64).sum().item()))
+    ok_bands = True
+    if rank == 0:
+        whole = engine.develop(torch.from_numpy(frame.view(np.int16)).to(dev), **kw)
+        for (bb, ee, s) in checks:
+            ok_bands &= (whole[bb:ee].view(torch.int32).to(torch.int64).sum().item() == s)
+        ok_bands &= bool(torch.equal(whole[b:e].view(torch.int32), out.view(torch.int32)))
+        del whole
+    # --- HDR brackets spread over ranks (config 4) ---
+    Hh, Wh, nb = 4000, 6000, 5
+    base = (np.tile(syn.scene(Hh // 4, Wh // 4, 5), (4, 4)).astype(np.float32) - 512.0) / 16383.0
+    evs = [8.0, 9.0, 10.0, 11.0, 12.0]
+    mine = {}
+    for k in range(nb):
+        if k % world == rank:
+            mine[k] = torch.from_numpy(np.clip(base * np.float32(2.0 ** (2 - k)), 0, 1).astype(np.float32)).to(dev)
+    halo = parallel.halo_rows(stages)
+    tev, offs, bias = fusion_constants(evs, wb)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    rows, hb = parallel.exchange_brackets_by_rows(mine, nb, Hh, halo, like=torch.empty((0, Wh), dtype=torch.float32, device=dev))
+    fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
+    bb, be = parallel.band_rows(Hh, world, rank)
+    hdr_out = engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=Hh, in_row0=hb)
+    torch.cuda.synchronize(); dist.barrier()
+    t_hdr = time.perf_counter() - t0
+    sums = [None] * world
+    dist.all_gather_object(sums, (bb, be, hdr_out.view(torch.int32).to(torch.int64).sum().item()))
+    ok_hdr = True
+    if rank == 0:
+        allb = [torch.from_numpy(np.clip(base * np.float32(2.0 ** (2 - k)), 0, 1).astype(np.float32)).to(dev) for k in range(nb)]
+        f1, _ = engine.fuse_exposures(allb, offs, bias, int(np.argmax(offs)), want_count=False)
+        whole = engine.develop(f1, wb, m, stages=stages, hdr=True)
+        for (x0, x1, s) in sums:
+            ok_hdr &= (whole[x0:x1].view(torch.int32).to(torch.int64).sum().item() == s)
+        print(json.dumps({"n_gpus": world, "bands_100MP_bit_identical": bool(ok_bands), "bands_100MP_s": t_band,
+                          "bands_100MP_Mpix_s": H * W / t_band / 1e6, "hdr5_24MP_bit_identical": bool(ok_hdr),
+                          "hdr5_24MP_s": t_hdr}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
