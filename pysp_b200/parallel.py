@@ -40,6 +40,11 @@ def band_with_halo(height, world, rank, stages):
     return b, e, max(0, b - h), min(height, e + h)
 
 
+def _bytes(t):
+    """Raw rows travel as bytes: NCCL has no 16-bit integer type, and the payload is opaque anyway."""
+    return t.view(torch.uint8) if t.dtype in (torch.int16, torch.uint16) else t
+
+
 def exchange_halo(band, height, stages, group=None):
     """band: [rows, W] tensor holding exactly this rank's band rows.  Returns ([held_rows, W] tensor,
     held_begin): the band extended by the neighbours' raw rows.  Bands shorter than the halo pull from
@@ -58,13 +63,13 @@ def exchange_halo(band, height, stages, group=None):
         # rows of mine that the peer needs
         s0, s1 = max(b, phb), min(e, phe)
         if s0 < s1:
-            t = band[s0 - b:s1 - b].contiguous()
+            t = _bytes(band[s0 - b:s1 - b].contiguous())
             keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, peer, group))
         # rows of the peer that I need
         r0, r1 = max(pb, hb), min(pe, he)
         if r0 < r1:
-            ops.append(dist.P2POp(dist.irecv, held[r0 - hb:r1 - hb], peer, group))
+            ops.append(dist.P2POp(dist.irecv, _bytes(held[r0 - hb:r1 - hb]), peer, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
