@@ -44,12 +44,17 @@ extern "C" {
 #define PYSP_OUT_LIN_F32 1 /* ... .to_lin_srgb() (base_types/image_base.py:62-64) */
 #define PYSP_OUT_LIN_F16 2 /* same, stored as half */
 
+/* const.py:3-6 (QualityDemosaic); Draft is not on the B200 path */
+#define PYSP_QUALITY_BEST 0
+#define PYSP_QUALITY_FAST 1
+
 #define PYSP_MAX_BRACKETS 16
 
 /* One develop call = RawBayerData.demosaic(QualityDemosaic.Best, stages) [+ .to_lin_srgb()
  * [+ lin_srgb_to_srgb]] on one frame or one row band of it.
  * Replaces: image.py:191-197 (to_rggb, demosaic), image.py:156-183 (dispatch, un-flip),
  * debayer/ahd.py:14-170 (debayer_ahd incl. the Cython build_map, ahd_homogeneity_cython.pyx:61),
+ * debayer/edge_assisted_gaussian.py:188-201 (debayer_eag) for PYSP_QUALITY_FAST,
  * normalization.py:4-25 when in_kind == PYSP_IN_U16, base_types/image_base.py:62-64 and
  * colorize/transform.py:21-53,76-99 for the PYSP_OUT_LIN_* kinds. */
 typedef struct pysp_develop_args {
@@ -73,7 +78,9 @@ typedef struct pysp_develop_args {
     int32_t row_begin, row_end;  /* stored rows to produce, even; whole frame = [0, height) */
     void* scratch;               /* >= pysp_develop_scratch_bytes(...) bytes when stages > 0 */
     int64_t scratch_bytes;
-    const void* lab_lut;         /* device copy of the table packed by pysp_lab_lut_pack_host */
+    const void* lab_lut;         /* device copy of the table packed by pysp_lab_lut_pack_host (Best only) */
+    int32_t quality;             /* PYSP_QUALITY_BEST: debayer_ahd; PYSP_QUALITY_FAST: debayer_eag
+                                    (debayer/edge_assisted_gaussian.py:188-201; stages and is_hdr are ignored) */
 } pysp_develop_args;
 
 int pysp_develop(const pysp_develop_args* args, void* stream);

@@ -443,3 +443,45 @@ def fuse_exposures(brackets, evs, wb, target_ev=None):
         q = np.divide(sum_p, sum_w)
     out = np.where(sum_w == 0, brightest, q)
     return out.astype(f32), cnt, max(offs), target_ev
+
+
+# ----------------------------------------------------------------------------------------------
+# QualityDemosaic.Fast: edge-assisted Gaussian (debayer/edge_assisted_gaussian.py:10-201)
+# ----------------------------------------------------------------------------------------------
+def delta_mix(top, bottom, left, right):
+    """edge_assisted_gaussian.py:10-49: bilinear in-fill weighted towards the direction of least change."""
+    dy = np.abs(top - bottom)
+    dx = np.abs(left - right)
+    total = dy + dx
+    avg_x = (left + right) / 2
+    avg_y = (top + bottom) / 2
+    sy = np.divide(dy, total, out=np.ones_like(total) * 0.5, where=total != 0)
+    sx = 1 - sy
+    return avg_y * sx + avg_x * sy
+
+
+def eag_demosaic(sensor, wb, backend="spec"):
+    """debayer_eag (edge_assisted_gaussian.py:188-201) on an RGGB float32 mosaic -> camera RGB float32."""
+    be = _Cv2Backend() if backend == "cv2" else _SpecBackend()
+    sensor = np.asarray(sensor, dtype=f32)
+    wb = np.asarray(wb, dtype=f32)
+    r, g1, b, g2 = split_planes(sensor)
+    p1, p2 = np.pad(g1, 1, mode="edge"), np.pad(g2, 1, mode="edge")
+    I = slice(1, -1)
+    g_at_b = delta_mix(p1[I, I], p1[2:, I], p2[I, I], p2[I, 2:])          # l.95-98
+    g_at_r = delta_mix(p2[:-2, I], p2[I, I], p1[I, :-2], p1[I, I])        # l.101-104
+    g_up = join_planes(g_at_r, g1, g_at_b, g2) * wb[1]                     # l.124, 193
+    rw, bw = r * wb[0], b * wb[2]
+    hf = g_up - be.gauss3(g_up)                                            # l.157
+    g_r, _, g_b, _ = split_planes(g_up)
+    r_up = resample_channel(rw, g_r, hf, False, be.corr)
+    b_up = resample_channel(bw, g_b, hf, True, be.corr)
+    return np.dstack((r_up, g_up, b_up)).astype(f32)
+
+
+def develop_fast(raw_u16, black, white, wb, mat_xyz_to_cam, white_xyz, pattern="RGGB", backend="spec"):
+    """RawBayerData.demosaic(QualityDemosaic.Fast).to_lin_srgb() (image.py:171-172)."""
+    m = cam_to_lin_srgb_matrix(mat_xyz_to_cam, white_xyz)
+    cam = eag_demosaic(to_rggb(normalize(raw_u16, black, white), pattern), wb, backend)
+    cam = np.ascontiguousarray(to_rggb(cam, pattern))
+    return to_lin_srgb(cam, m, backend), cam

@@ -5,7 +5,7 @@ Drop-in names (reference module in brackets):
     BayerPattern, RawDemosaicData                                              [base_types/image_base.py]
     QualityDemosaic                                                            [const.py]
     bayer_normalize                                                            [normalization.py]
-    debayer_ahd                                                                [debayer/__init__.py]
+    debayer_ahd, debayer_eag                                                   [debayer/__init__.py]
     cam_to_lin_srgb, cam_to_rgb_norm, clip_rgb, lin_srgb_to_srgb               [colorize/transform.py]
     fuse_exposures_to_raw                                                      [raw_hdr.py]
 The compute path is hand-written CUDA (sm_100a) behind a C ABI (include/pysp_b200.h); there is no CPU
@@ -21,7 +21,7 @@ def __getattr__(name):
         "RawBayerData": ".image", "RawRggbBayerData": ".image", "RawBayerDataFromRaw": ".image",
         "RawRgbgDataFromRaw": ".image", "reversible_transform_rggb": ".image",
         "BayerPattern": ".base_types.image_base", "RawDemosaicData": ".base_types.image_base",
-        "bayer_normalize": ".normalization", "debayer_ahd": ".debayer",
+        "bayer_normalize": ".normalization", "debayer_ahd": ".debayer", "debayer_eag": ".debayer",
         "cam_to_lin_srgb": ".colorize.transform", "cam_to_rgb_norm": ".colorize.transform",
         "clip_rgb": ".colorize.transform", "lin_srgb_to_srgb": ".colorize.transform",
         "fuse_exposures_to_raw": ".raw_hdr", "CameraWhiteBalance": ".wb_cct.cam_wb",

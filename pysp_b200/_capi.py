@@ -12,6 +12,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 CFA = {"RGGB": 1, "BGGR": 2, "GRBG": 3, "GBRG": 4}
 IN_U16, IN_F32 = 0, 1
 OUT_CAM_F32, OUT_LIN_F32, OUT_LIN_F16 = 0, 1, 2
+QUALITY_BEST, QUALITY_FAST = 0, 1
 MAX_BRACKETS = 16
 
 
@@ -29,6 +30,7 @@ class DevelopArgs(C.Structure):
         ("row_begin", C.c_int32), ("row_end", C.c_int32),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
         ("lab_lut", C.c_void_p),
+        ("quality", C.c_int32),
     ]
 
 
@@ -92,7 +94,7 @@ def check(rc, last_error=None):
 
 def fill_develop_args(height, width, pattern, in_kind, in_ptr, in_pitch, in_row0, in_rows, black, white, wb,
                       cam_to_srgb, stages, is_hdr, gamma, out_kind, out_ptr, out_pitch, out_row0, row_begin,
-                      row_end, scratch_ptr, scratch_bytes, lut_ptr):
+                      row_end, scratch_ptr, scratch_bytes, lut_ptr, quality=0):
     a = DevelopArgs()
     a.height, a.width = int(height), int(width)
     if isinstance(pattern, str):
@@ -123,4 +125,5 @@ def fill_develop_args(height, width, pattern, in_kind, in_ptr, in_pitch, in_row0
     a.scratch = scratch_ptr
     a.scratch_bytes = int(scratch_bytes)
     a.lab_lut = lut_ptr
+    a.quality = int(quality)
     return a

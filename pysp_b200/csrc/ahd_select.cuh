@@ -246,8 +246,10 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
                                            : ((const float*)stage)[si];
             }
         }
-        Q[L::P_R * QN + it] = v[0] * p.c.wb[0]; Q[L::P_G1 * QN + it] = v[1] * p.c.wb[1];
-        Q[L::P_G2 * QN + it] = v[2] * p.c.wb[1]; Q[L::P_B * QN + it] = v[3] * p.c.wb[2];
+        // the Fast demosaic interpolates the un-balanced greens and balances afterwards (eag.cuh)
+        const float wbg = p.algo == ALGO_EAG ? 1.0f : p.c.wb[1];
+        Q[L::P_R * QN + it] = v[0] * p.c.wb[0]; Q[L::P_G1 * QN + it] = v[1] * wbg;
+        Q[L::P_G2 * QN + it] = v[2] * wbg; Q[L::P_B * QN + it] = v[3] * p.c.wb[2];
     }
 }
 

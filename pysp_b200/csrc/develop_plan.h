@@ -92,13 +92,17 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad in_kind %d", a->in_kind);
     if (a->out_kind < PYSP_OUT_CAM_F32 || a->out_kind > PYSP_OUT_LIN_F16)
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad out_kind %d", a->out_kind);
-    if (!a->in || !a->out || !a->lab_lut) return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: null buffer");
+    if (!a->in || !a->out || (!a->lab_lut && a->quality == PYSP_QUALITY_BEST))
+        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: null buffer");
     const int rb = a->row_begin, re = a->row_end;
     if (rb < 0 || re > H || rb >= re || (rb & 1) || (re & 1))
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: row band [%d,%d) must be even and inside the frame", rb, re);
     if (a->out_row0 > rb)
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: out_row0 %d is past row_begin %d", a->out_row0, rb);
-    const int S = a->stages > 0 ? a->stages : 0;                 // debayer/ahd.py:163
+    if (a->quality != PYSP_QUALITY_BEST && a->quality != PYSP_QUALITY_FAST)
+        return plan_fail(err, errn, PYSP_ERR_UNSUPPORTED, "Quality mode not implemented: %d", a->quality);   // image.py:176
+    // postprocess steps are "ignored unless using Best quality" (image.py:163)
+    const int S = (a->quality == PYSP_QUALITY_BEST && a->stages > 0) ? a->stages : 0;      // debayer/ahd.py:163
     if (S > PYSP_MAX_STAGES)
         return plan_fail(err, errn, PYSP_ERR_UNSUPPORTED, "pysp_develop: at most %d postprocess stages", PYSP_MAX_STAGES);
     const int64_t esz = a->in_kind == PYSP_IN_U16 ? 2 : 4;
@@ -165,6 +169,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         sp.fast_div = fast_division_is_exact(sp.black, sp.white) ? 1 : 0;
     }
     sp.lut = (const uint4*)a->lab_lut;
+    sp.algo = a->quality == PYSP_QUALITY_FAST ? ALGO_EAG : ALGO_AHD;
     sp.y_begin = k1b; sp.y_end = k1e;
     sp.tiles_x = (W + tw1 - 1) / tw1;
     sp.n_tiles = sp.tiles_x * ((k1e - k1b + th1 - 1) / th1);

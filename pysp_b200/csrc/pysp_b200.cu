@@ -12,6 +12,7 @@
 
 #include "../../include/pysp_b200.h"
 #include "ahd_select.cuh"
+#include "eag.cuh"
 #include "median_stage.cuh"
 #include "pointwise.cuh"
 #include "develop_plan.h"
@@ -49,6 +50,8 @@ __device__ __forceinline__ void store_tile(const float* out, const StoreParams& 
 // K1, persistent: grid = resident CTAs; each CTA walks tiles blockIdx.x, +gridDim.x, ...  The raw box of the next
 // tile is in flight (TMA -> staging, mbarrier) while phases 1-4 of the current tile run; the finished tile leaves
 // through the staging tile by TMA store, overlapped with the next tile's phases 0-3.
+// ALGO_EAG (QualityDemosaic.Fast) runs its own phases 1-2 (eag.cuh) in the same pipeline.
+template <int ALGO>
 __global__ void __launch_bounds__(K1_THREADS, 2)
 ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant__ CUtensorMap in_map,
                   const __grid_constant__ OutMaps out_maps) {
@@ -87,8 +90,15 @@ ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant_
         const int next = tile + gridDim.x;
         if (p.tma_in && next < p.n_tiles) fetch(next);
         auto before_out = [&]() { if (p.st.tma && threadIdx.x == 0) tma_store_wait_read(); };
-        if (edge) select_phases<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y, before_out);
-        else select_phases<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y, before_out);
+        if (ALGO == ALGO_EAG) {
+            before_out();
+            __syncthreads();
+            if (edge) eag_phases<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y);
+            else eag_phases<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y);
+        } else {
+            if (edge) select_phases<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y, before_out);
+            else select_phases<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y, before_out);
+        }
         if (p.st.tma) fence_async_smem();                 // staging tile written by the generic proxy, read by TMA
         __syncthreads();
         store_tile<K1_TW, K1_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K1_TW,
@@ -332,13 +342,15 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
     }
     const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
     {
-        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_AHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
         cudaError_t e2 = cudaFuncSetAttribute(median_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-        if (e1 != cudaSuccess || e2 != cudaSuccess)
-            return fail(PYSP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        cudaError_t e3 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_EAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+            return fail(PYSP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     }
+    const bool eag = plan.select.algo == ALGO_EAG;
     int grid1 = 0, grid2 = 0;
-    rc = resident_ctas((const void*)ahd_select_kernel, K1_THREADS, smem1, &grid1);
+    rc = resident_ctas(eag ? (const void*)ahd_select_kernel<ALGO_EAG> : (const void*)ahd_select_kernel<ALGO_AHD>, K1_THREADS, smem1, &grid1);
     if (rc) return rc;
     {
         CUtensorMap in_map;
@@ -352,8 +364,9 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
         if (rc) return rc;
         const int grid = plan.select.n_tiles < grid1 ? plan.select.n_tiles : grid1;
         {
-            TimedLaunch t(0, stream);
-            ahd_select_kernel<<<grid, K1_THREADS, smem1, stream>>>(plan.select, in_map, om);
+            TimedLaunch t(eag ? 2 : 0, stream);
+            if (eag) ahd_select_kernel<ALGO_EAG><<<grid, K1_THREADS, smem1, stream>>>(plan.select, in_map, om);
+            else ahd_select_kernel<ALGO_AHD><<<grid, K1_THREADS, smem1, stream>>>(plan.select, in_map, om);
         }
         rc = check_launch("ahd_select_kernel");
         if (rc) return rc;

@@ -74,6 +74,7 @@ struct View2D {          // plain description of a 2-D tensor (rows x cols eleme
 // rows of the band) or the scratch handed to the next median stage: three float planes r-g, b-g, g in logical
 // orientation (debayer/ahd.py:153-154 needs exactly these), so that the next stage loads them by TMA as is.
 enum OutMode { OUT_FINAL = 0, OUT_PLANES = 1 };
+enum Algo { ALGO_AHD = 0, ALGO_EAG = 1 };
 
 struct StoreParams {
     int mode;            // OutMode
@@ -96,6 +97,7 @@ struct SelectParams {    // K1: mosaic -> selected camera RGB
     float rwhite[4];     // float(1/white)
     int fast_div;        // 1: reciprocal + FMA correction verified equal to IEEE division for these levels
     const uint4* lut;    // paired-node Lab table (device), see lab_lookup
+    int algo;            // ALGO_AHD (QualityDemosaic.Best) or ALGO_EAG (QualityDemosaic.Fast)
     StoreParams st;
     int y_begin, y_end;  // logical rows to produce (even)
     int tiles_x, n_tiles;

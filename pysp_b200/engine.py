@@ -82,15 +82,21 @@ _OUT_KINDS = {"cam": _capi.OUT_CAM_F32, "lin": _capi.OUT_LIN_F32, "lin_f16": _ca
 
 
 def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white=None, hdr=False, gamma=False,
-            out="lin", out_tensor=None, rows=None, frame_height=None, in_row0=0, out_row0=None, stream=None):
+            out="lin", out_tensor=None, rows=None, frame_height=None, in_row0=0, out_row0=None, stream=None,
+            quality="best"):
     """Run the fused develop chain on one frame (or one row band of it) that is resident on the GPU.
 
     mosaic      CUDA tensor [rows_held, W]: uint16/int16 sensor counts (normalisation fused, needs
                 black/white in the reference order [TL,TR,BR,BL]) or float32 `sensor_scaled`.
     rows        (row_begin, row_end) of the stored frame to produce; default the whole frame.
     frame_height / in_row0   when `mosaic` holds only rows [in_row0, in_row0+rows_held) of a taller frame.
+    quality     "best" = AHD (debayer_ahd), "fast" = edge-assisted Gaussian (debayer_eag; stages/hdr ignored).
     Returns a CUDA tensor [row_end-row_begin, W, 3] (float32, or float16 for out="lin_f16").
     """
+    if quality not in ("best", "fast"):
+        raise NotImplementedError("Quality mode not implemented: %s" % str(quality))
+    if quality == "fast":
+        stages = 0
     require_cuda()
     L = _capi.lib()
     if not mosaic.is_cuda:
@@ -129,7 +135,8 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
             H, W, pattern, in_kind, mosaic.data_ptr(), mosaic.stride(0) * mosaic.element_size(), in_row0, held,
             black, white, wb, cam_to_srgb, stages, hdr, gamma, kind, out_tensor.data_ptr(),
             out_tensor.stride(0) * out_tensor.element_size(), out_row0, rb, re,
-            scratch.data_ptr() if scratch is not None else None, nscr, lut.data_ptr())
+            scratch.data_ptr() if scratch is not None else None, nscr, lut.data_ptr(),
+            quality=_capi.QUALITY_FAST if quality == "fast" else _capi.QUALITY_BEST)
         _capi.check(L.pysp_develop(C.byref(a), _stream_ptr(stream)))
     return out_tensor
 

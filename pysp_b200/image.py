@@ -14,7 +14,7 @@ from .base_types.image_base import (BayerPattern, RawBayerData_BaseType, RawDemo
                                     RawRggbBayerData_BaseType)
 from .colour import cam_to_rgb_matrix
 from .const import QualityDemosaic
-from .debayer import debayer_ahd
+from .debayer import debayer_ahd, debayer_eag
 from .normalization import bayer_normalize
 
 _PATTERN_NAME = {BayerPattern.Rggb: "RGGB", BayerPattern.Bggr: "BGGR", BayerPattern.Grbg: "GRBG",
@@ -34,18 +34,23 @@ def reversible_transform_rggb(sensor_data, bayer_pattern):
 
 
 def _demosaic_dispatch(quality):
+    """image.py:169-176: Best -> debayer_ahd, Fast -> debayer_eag; Draft (cv2.resize based) is not on the B200 path."""
     if quality == QualityDemosaic.Best:
-        return
-    if quality in (QualityDemosaic.Fast, QualityDemosaic.Draft):
-        raise NotImplementedError("Quality mode not implemented on the B200 path yet: %s" % str(quality))
+        return "best"
+    if quality == QualityDemosaic.Fast:
+        return "fast"
+    if quality == QualityDemosaic.Draft:
+        raise NotImplementedError("Quality mode not implemented on the B200 path: %s" % str(quality))
     raise NotImplementedError("Quality mode not implemented: %s" % str(quality))
 
 
 class RawRggbBayerData(RawRggbBayerData_BaseType):
     def demosaic(self, quality, postprocess_steps=1):
         """Demosaic to a new RawDemosaicData; the source is not modified."""
-        _demosaic_dispatch(quality)
-        debayered = debayer_ahd(self, postprocess_stages=postprocess_steps)
+        if _demosaic_dispatch(quality) == "fast":
+            debayered = debayer_eag(self)
+        else:
+            debayered = debayer_ahd(self, postprocess_stages=postprocess_steps)
         debayered.image = reversible_transform_rggb(debayered.image, self.source_pattern)
         return debayered
 
@@ -74,7 +79,7 @@ class RawBayerData(RawBayerData_BaseType):
     def demosaic(self, quality, postprocess_steps=1):
         """to_rggb().demosaic(...), as one kernel chain: the CFA flip is index math on load and store, and
         16-bit counts (from_mosaic) are normalised inside the kernel."""
-        _demosaic_dispatch(quality)
+        q = _demosaic_dispatch(quality)
         wb = self.cam_wb.get_reciprocal_multipliers()
         mat = self.cam_wb.get_matrix()
         stages = max(int(postprocess_steps), 0)
@@ -84,11 +89,11 @@ class RawBayerData(RawBayerData_BaseType):
         if self._counts is not None:
             want_np = self._counts_numpy
             cam = engine.develop(as_cuda(self._counts), wb, cam_to_rgb_matrix(mat), stages=stages, pattern=pattern,
-                                 black=self._levels[0], white=self._levels[1], out="cam")
+                                 black=self._levels[0], white=self._levels[1], out="cam", quality=q)
         else:
             want_np = is_numpy(self.sensor_scaled)
             cam = engine.develop(as_cuda(self.sensor_scaled, torch.float32), wb, cam_to_rgb_matrix(mat),
-                                 stages=stages, pattern=pattern, out="cam")
+                                 stages=stages, pattern=pattern, out="cam", quality=q)
         out = RawDemosaicData(give_back(cam, want_np), wb, wb_norm=False)
         out.mat_xyz = mat
         out.current_ev = self.current_ev
@@ -96,7 +101,7 @@ class RawBayerData(RawBayerData_BaseType):
 
     debayer = demosaic          # README spelling
 
-    def develop(self, postprocess_steps=1, srgb_gamma=False, half=False):
+    def develop(self, postprocess_steps=1, srgb_gamma=False, half=False, quality=QualityDemosaic.Best):
         """demosaic(QualityDemosaic.Best, n).to_lin_srgb() [-> lin_srgb_to_srgb] as ONE fused chain: the
         clip + float64 camera->linear-sRGB matrix (+ gamma) run in the last kernel's epilogue, so the
         linear-sRGB image is the only thing written to HBM."""
@@ -107,14 +112,15 @@ class RawBayerData(RawBayerData_BaseType):
             raise NotImplementedError(str(self.sensor_pattern) + " not implemented!")
         kind = "lin_f16" if half else "lin"
         stages = max(int(postprocess_steps), 0)
+        q = _demosaic_dispatch(quality)
         if self._counts is not None:
             want_np = self._counts_numpy
             out = engine.develop(as_cuda(self._counts), wb, m, stages=stages, pattern=pattern, black=self._levels[0],
-                                 white=self._levels[1], gamma=srgb_gamma, out=kind)
+                                 white=self._levels[1], gamma=srgb_gamma, out=kind, quality=q)
         else:
             want_np = is_numpy(self.sensor_scaled)
             out = engine.develop(as_cuda(self.sensor_scaled, torch.float32), wb, m, stages=stages, pattern=pattern,
-                                 gamma=srgb_gamma, out=kind)
+                                 gamma=srgb_gamma, out=kind, quality=q)
         return give_back(out, want_np)
 
 

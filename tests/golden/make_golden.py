@@ -26,6 +26,24 @@ from pysp_b200 import synthetic as syn  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def run_reference_fast(raw, black, white, pattern="RGGB"):
+    """RawBayerData.demosaic(QualityDemosaic.Fast) -> camera RGB and linear sRGB (image.py:171-172)."""
+    rh.load()
+    from pySP.normalization import bayer_normalize
+    from pySP.image import RawBayerData
+    from pySP.base_types.image_base import BayerPattern
+    from pySP.const import QualityDemosaic
+    img = RawBayerData()
+    img.sensor_scaled = bayer_normalize(raw, list(black), list(white))
+    img.sensor_pattern = {"RGGB": BayerPattern.Rggb, "BGGR": BayerPattern.Bggr, "GRBG": BayerPattern.Grbg,
+                          "GBRG": BayerPattern.Gbrg}[pattern]
+    img.cam_wb = rh.StubWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    img.current_ev = 10.0
+    dem = img.demosaic(QualityDemosaic.Fast)
+    cam = np.array(dem.image, dtype=np.float32, copy=True)
+    return dict(cam=cam, lin=dem.to_lin_srgb().astype(np.float32))
+
+
 def run_reference(raw, black, white, stages, pattern="RGGB", mat=syn.MAT_XYZ_TO_CAM, xyz=syn.WHITE_XYZ,
                   sensor_override=None, hdr=False):
     import cv2
@@ -91,6 +109,15 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), raw=raw, black=np.array(black),
                             white=np.array(white), stages=stages, pattern=pat, **res, **meta)
         print(name, res["lin"].shape, "pick_h frac %.3f" % res["pick_h"].mean())
+
+    # QualityDemosaic.Fast (edge-assisted Gaussian)
+    for name, raw, pat in (("fast_rand8x8", syn.random_mosaic(8, 8, 21), "RGGB"), ("fast_scene34x50", syn.scene(34, 50, 22), "RGGB"),
+                           ("fast_scene64x96_GBRG", syn.scene(64, 96, 23), "GBRG"), ("fast_flat20x28", np.full((20, 28), 7000, np.uint16), "RGGB"),
+                           ("fast_rand66x130", syn.random_mosaic(66, 130, 24), "BGGR")):
+        res = run_reference_fast(raw, syn.BLACK, syn.WHITE, pat)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), raw=raw, black=np.array(syn.BLACK), white=np.array(syn.WHITE),
+                            pattern=pat, **res, **meta)
+        print(name, res["lin"].shape)
 
     # HDR: f32 mosaic with values up to 3.0, HDR flag set (debayer/ahd.py:52-59)
     rng = np.random.default_rng(9)

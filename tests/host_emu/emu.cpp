@@ -15,6 +15,7 @@
 struct uint4 { unsigned int x, y, z, w; };
 
 #include "../../pysp_b200/csrc/ahd_select.cuh"
+#include "../../pysp_b200/csrc/eag.cuh"
 #include "../../pysp_b200/csrc/median_stage.cuh"
 #include "../../pysp_b200/csrc/develop_plan.h"
 
@@ -39,12 +40,13 @@ static void run_chain(const DevelopPlan& plan) {
             int bx, by;
             select_input_box<TW, TH>(p, tx, ty, &bx, &by);
             box_load_generic(smem + LS::OFF_STAGE, p.in, bx, by, LS::BOXW, LS::BOXH);
+            const bool eag = p.algo == ALGO_EAG;
             if (select_tile_is_edge<TW, TH>(p, tx, ty)) {
                 select_phase0<TW, TH, true>(p, smem, tx, ty);
-                select_phases<TW, TH, true>(p, smem, tx, ty, []() {});
+                if (eag) eag_phases<TW, TH, true>(p, smem, tx, ty); else select_phases<TW, TH, true>(p, smem, tx, ty, []() {});
             } else {
                 select_phase0<TW, TH, false>(p, smem, tx, ty);
-                select_phases<TW, TH, false>(p, smem, tx, ty, []() {});
+                if (eag) eag_phases<TW, TH, false>(p, smem, tx, ty); else select_phases<TW, TH, false>(p, smem, tx, ty, []() {});
             }
             store_tile_generic<TW, TH>((const float*)(smem + LS::OFF_OUT), p.st, p.g, tx * TW, p.y_begin + ty * TH);
         }

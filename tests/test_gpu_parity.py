@@ -207,6 +207,35 @@ def test_generic_paths(mode):
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("name", ["fast_rand8x8", "fast_scene34x50", "fast_scene64x96_GBRG", "fast_flat20x28", "fast_rand66x130"])
+def test_fast_quality(eng, name):
+    """QualityDemosaic.Fast: RawBayerData.demosaic(Fast).to_lin_srgb() against the reference's golden outputs."""
+    import pysp_b200 as P
+    from pysp_b200.wb_cct import CameraWhiteBalance
+    d = golden(name)
+    wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    img = P.RawRgbgDataFromRaw.from_mosaic(d["raw"], list(d["black"]), list(d["white"]), str(d["pattern"]).capitalize(), wb, ev=10.0)
+    dem = img.demosaic(P.QualityDemosaic.Fast, postprocess_steps=3)
+    assert_bit_equal(dem.image, d["cam"], "Fast camera RGB")
+    assert_bit_equal(dem.to_lin_srgb(), d["lin"], "Fast linear sRGB")
+    assert_bit_equal(img.develop(quality=P.QualityDemosaic.Fast), d["lin"], "Fast fused develop")
+    img2 = P.RawBayerData()
+    img2.sensor_scaled = P.bayer_normalize(d["raw"], list(d["black"]), list(d["white"]))
+    img2.sensor_pattern = img.sensor_pattern
+    img2.cam_wb = wb
+    img2.current_ev = 10.0
+    assert_bit_equal(img2.to_rggb().demosaic(P.QualityDemosaic.Fast).image, d["cam"], "Fast via RawRggbBayerData")
+
+
+def test_fast_quality_24mp(eng):
+    raw = syn.scene(1200, 1808, 3)
+    lin, _ = sp.develop_fast(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    t = eng.to_device(raw)
+    out = eng.develop(t, WB, M, black=syn.BLACK, white=syn.WHITE, quality="fast")
+    torch.cuda.synchronize()
+    assert_bit_equal(out.cpu().numpy(), lin, "Fast 2 MP frame")
+
+
 def test_large_frame_smoke(eng):
     """100 MP frame (config 5): runs, finite, deterministic checksum across two runs."""
     H, W = 8660, 11548

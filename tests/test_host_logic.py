@@ -51,7 +51,7 @@ def test_quality_dispatch_errors(colour_setup):
     with pytest.raises(NotImplementedError):
         img.demosaic("nonsense")
     with pytest.raises(NotImplementedError):
-        img.demosaic(QualityDemosaic.Fast)
+        img.demosaic(QualityDemosaic.Draft)
     raw = RawBayerData()
     raw.sensor_scaled = np.zeros((8, 8), dtype=np.float32)
     raw.sensor_pattern = BayerPattern.Rggb

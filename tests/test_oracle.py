@@ -81,3 +81,11 @@ def test_cv2_backend_is_close():
     b, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 0, backend="cv2")
     close = np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-3)
     assert close.mean() > 0.995
+
+
+@pytest.mark.parametrize("name", ["fast_rand8x8", "fast_scene34x50", "fast_scene64x96_GBRG", "fast_flat20x28", "fast_rand66x130"])
+def test_fast_quality_matches_reference(name):
+    d = golden(name)
+    lin, cam = sp.develop_fast(d["raw"], d["black"], d["white"], WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, str(d["pattern"]))
+    assert_bit_equal(cam, d["cam"], "Fast camera RGB")
+    assert_bit_equal(lin, d["lin"], "Fast linear sRGB")

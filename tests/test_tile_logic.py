@@ -48,7 +48,7 @@ LUT = packed_lut()
 
 
 def emu_develop(lib, src, stages, pattern="RGGB", tile=(16, 8), black=syn.BLACK, white=syn.WHITE,
-                out_kind=_capi.OUT_LIN_F32, band=None, hdr=False, held=None):
+                out_kind=_capi.OUT_LIN_F32, band=None, hdr=False, held=None, quality=0):
     """src: uint16 counts or float32 sensor; `held` = (row0, rows) keeps only that slice of the frame."""
     H, W = src.shape
     rb, re = band or (0, H)
@@ -60,7 +60,7 @@ def emu_develop(lib, src, stages, pattern="RGGB", tile=(16, 8), black=syn.BLACK,
     a = _capi.fill_develop_args(H, W, pattern, _capi.IN_U16 if src.dtype == np.uint16 else _capi.IN_F32,
                                 part.ctypes.data, part.strides[0], r0, nr, black, white, WB, M, stages, hdr, False,
                                 out_kind, out.ctypes.data, out.strides[0], rb, rb, re, scratch.ctypes.data,
-                                scratch.nbytes, LUT.ctypes.data)
+                                scratch.nbytes, LUT.ctypes.data, quality=quality)
     rc = lib.emu_develop(C.byref(a), tile[0], tile[1])
     assert rc == 0, lib.emu_last_error()
     return out
@@ -112,3 +112,24 @@ def test_golden_through_emulation(emu):
     d = golden("scene64x96_BGGR")
     out = emu_develop(emu, d["raw"], int(d["stages"]), "BGGR", black=d["black"], white=d["white"])
     assert_bit_equal(out, d["lin"], "golden BGGR")
+
+
+@pytest.mark.parametrize("name", ["fast_rand8x8", "fast_scene34x50", "fast_scene64x96_GBRG", "fast_flat20x28", "fast_rand66x130"])
+def test_fast_quality_golden(emu, name):
+    """QualityDemosaic.Fast (edge-assisted Gaussian) against the reference's golden outputs."""
+    from conftest import golden
+    d = golden(name)
+    for tile in ((16, 8), (56, 28)):
+        cam = emu_develop(emu, d["raw"], 3, str(d["pattern"]), tile=tile, out_kind=_capi.OUT_CAM_F32, quality=1)
+        assert_bit_equal(cam, d["cam"], "Fast camera RGB %s" % (tile,))
+        assert_bit_equal(emu_develop(emu, d["raw"], 0, str(d["pattern"]), tile=tile, quality=1), d["lin"], "Fast linear sRGB")
+
+
+def test_fast_quality_bands(emu):
+    raw = syn.scene(48, 72, 12)
+    whole = emu_develop(emu, raw, 0, quality=1)
+    lin, _ = sp.develop_fast(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    assert_bit_equal(whole, lin, "Fast vs oracle")
+    for rb, re in ((0, 20), (20, 48)):
+        r0, r1 = max(0, rb - 6), min(48, re + 6)
+        assert_bit_equal(emu_develop(emu, raw, 0, band=(rb, re), held=(r0, r1 - r0), quality=1), whole[rb:re], "Fast band")
