@@ -264,8 +264,13 @@ def main():
         dom = max(per, key=lambda k: per[k])
         chain_ms = sum(per.values())
         ach = ALGO_BYTES_PER_PX[dom] * px_per_frame / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom] * px_per_frame,
                     "ms_per_launch": per, "launches": {names[k]: int(cnt[k]) for k in range(2)},
                     "chain": {"bytes_per_px": 14.0, "ms_per_frame": chain_ms,
