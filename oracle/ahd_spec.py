@@ -121,14 +121,44 @@ def normalize(raw, black, white):
     return join_planes(*out)
 
 
+_FMA_LIB = None
+
+
+def build_c(force=False):
+    """Compile the C part of the oracle (oracle/csrc/dot3_fma.c) with gcc into oracle/_build/."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "csrc", "dot3_fma.c")
+    so = os.path.join(here, "_build", "liboracle_dot3.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([gcc, "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so, "-lm"])
+    return so
+
+
+def _fma_lib():
+    global _FMA_LIB
+    if _FMA_LIB is None:
+        import ctypes
+        lib = ctypes.CDLL(build_c())
+        lib.oracle_dot3_fma.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        lib.oracle_dot3_fma.restype = None
+        _FMA_LIB = lib
+    return _FMA_LIB
+
+
 def mat3_f64(rgb, m):
-    """f32( M . rgb ) with products and left-to-right sums in float64 (colorize/transform.py:52-53).
-    Canonical order for the oracle and the CUDA path: ((m0*c0 + m1*c1) + m2*c2), unfused."""
-    c = rgb.astype(np.float64)
-    out = np.empty(rgb.shape, dtype=f32)
-    for k in range(3):
-        acc = (m[k, 0] * c[..., 0] + m[k, 1] * c[..., 1]) + m[k, 2] * c[..., 2]
-        out[..., k] = acc.astype(f32)
+    """f32( M . rgb ) accumulated in float64 as the reference's `np.dot(rgb, M.T)` does (colorize/transform.py:52-53):
+    OpenBLAS dgemm runs a fused multiply-add chain over k, acc = m0*c0; acc = fma(m1, c1, acc); acc = fma(m2, c2, acc).
+    That is the canonical order of the oracle and of the CUDA path; it is pinned by tests/golden/dot_fma_pins.npz
+    (inputs where the fused and unfused sums round to different float32 values).  The correctly rounded fma() comes
+    from C (oracle/csrc/dot3_fma.c) -- NumPy has no fused multiply-add."""
+    c = np.ascontiguousarray(rgb, dtype=f32)
+    mm = np.ascontiguousarray(m, dtype=np.float64)
+    out = np.empty(c.shape, dtype=f32)
+    if c.size:
+        _fma_lib().oracle_dot3_fma(c.ctypes.data, c.size // 3, mm.ctypes.data, out.ctypes.data)
     return out
 
 

@@ -121,15 +121,19 @@ PYSP_HD int reflect101(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 -
 // keeps the CFA phase.
 PYSP_HD int phase_clamp(int v, int n) { return v < 0 ? (v & 1) : (v >= n ? n - 2 + (v & 1) : v); }
 
-// ---- float64 3x3, canonical order ((m0*c0 + m1*c1) + m2*c2), unfused; result rounded to float32 ------
+// ---- float64 3x3, result rounded to float32 ---------------------------------------------------------
+// Accumulation order of the reference's np.dot (OpenBLAS dgemm, K = 3): acc = m0*c0; acc = fma(m1, c1, acc);
+// acc = fma(m2, c2, acc) -- pinned by tests/golden/dot_fma_pins.npz (colorize/transform.py:52-53).
 PYSP_HD float dot3_f64(const double* m, float c0, float c1, float c2) {
 #ifdef __CUDA_ARCH__
-    double a = __dadd_rn(__dmul_rn(m[0], (double)c0), __dmul_rn(m[1], (double)c1));
-    return __double2float_rn(__dadd_rn(a, __dmul_rn(m[2], (double)c2)));
+    double a = __dmul_rn(m[0], (double)c0);
+    a = __fma_rn(m[1], (double)c1, a);
+    return __double2float_rn(__fma_rn(m[2], (double)c2, a));
 #else
-    volatile double p0 = m[0] * (double)c0, p1 = m[1] * (double)c1, p2 = m[2] * (double)c2;
-    volatile double a = p0 + p1;
-    return (float)(a + p2);
+    volatile double a = m[0] * (double)c0;
+    a = fma(m[1], (double)c1, a);
+    a = fma(m[2], (double)c2, a);
+    return (float)a;
 #endif
 }
 

@@ -128,6 +128,8 @@ def test_pointwise_entry_points(eng):
     x = np.random.default_rng(0).uniform(-0.5, 1.5, size=(33, 17, 3)).astype(np.float32)
     assert_bit_equal(cam_to_lin_srgb(x, wb.get_matrix(), clip_highlights=False), sp.mat3_f64(x, M), "unclipped matrix")
     assert_bit_equal(clip_rgb(x), np.clip(x, 0, 1), "clip_rgb")
+    pins = golden("dot_fma_pins")       # float64 accumulation order of the reference's np.dot (FMA chain)
+    assert_bit_equal(cam_to_lin_srgb(pins["x"], wb.get_matrix()), pins["y"], "cam_to_lin_srgb on the accumulation-order pins")
     g = golden("gamma")
     y = lin_srgb_to_srgb(g["x"])
     assert np.all(np.abs(y - g["y"]) <= 1e-4 * np.maximum(np.abs(g["y"]), 1e-3))

@@ -89,3 +89,16 @@ def test_fast_quality_matches_reference(name):
     lin, cam = sp.develop_fast(d["raw"], d["black"], d["white"], WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, str(d["pattern"]))
     assert_bit_equal(cam, d["cam"], "Fast camera RGB")
     assert_bit_equal(lin, d["lin"], "Fast linear sRGB")
+
+
+def test_matrix_accumulation_order_pins():
+    """colorize/transform.py:52-53: the float64 3x3 is an FMA chain (OpenBLAS dgemm).  The fixture holds inputs on
+    which fused and unfused accumulation round to different float32 values, with the unmodified reference's
+    outputs (tests/golden/make_fma_pins.py): the oracle must equal the reference, i.e. the fused variant."""
+    d = golden("dot_fma_pins")
+    m = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    assert np.array_equal(m, d["m"])
+    assert_bit_equal(sp.to_lin_srgb(d["x"], m), d["y"], "camera -> linear sRGB on the accumulation-order pins")
+    n = d["x"].shape[1]
+    got = d["y"][0, np.arange(n), d["row"]]
+    assert n >= 20 and np.array_equal(got, d["fused"]) and not np.any(got == d["unfused"])
