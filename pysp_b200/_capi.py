@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpysp_b200.so")
+# PYSP_B200_LIB: developer hook to load an A/B build of the same library (tools/kbench.py)
+LIB_PATH = os.environ.get("PYSP_B200_LIB") or os.path.join(_HERE, "libpysp_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 CFA = {"RGGB": 1, "BGGR": 2, "GRBG": 3, "GBRG": 4}

@@ -16,13 +16,15 @@ def sources():
     return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(HERE, "..", "include", "pysp_b200.h")]
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
-        return OUT
+def build(force=False, verbose=False, out=OUT, defines=()):
+    """`out` / `defines` build an A/B variant next to the product library (tools/kbench.py); the package itself
+    only ever loads libpysp_b200.so."""
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in sources()):
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd, cwd=os.path.join(HERE, "csrc"))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

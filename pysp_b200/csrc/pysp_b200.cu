@@ -19,8 +19,21 @@
 
 namespace pysp {
 
-constexpr int K1_TW = 56, K1_TH = 28, K1_THREADS = 256;
-constexpr int K2_TW = 60, K2_TH = 28, K2_THREADS = 256;
+// tile sizes (compile-time; the -D overrides exist for tools/kbench.py A/B builds)
+#ifndef PYSP_K1_TW
+#define PYSP_K1_TW 56
+#endif
+#ifndef PYSP_K1_TH
+#define PYSP_K1_TH 30
+#endif
+#ifndef PYSP_K2_TW
+#define PYSP_K2_TW 60
+#endif
+#ifndef PYSP_K2_TH
+#define PYSP_K2_TH 28
+#endif
+constexpr int K1_TW = PYSP_K1_TW, K1_TH = PYSP_K1_TH, K1_THREADS = 256;
+constexpr int K2_TW = PYSP_K2_TW, K2_TH = PYSP_K2_TH, K2_THREADS = 256;
 
 struct OutMaps { CUtensorMap m[3]; };     // final image: m[0]; planes: m[0..2]
 

@@ -210,8 +210,38 @@ PYSP_HD LabQ lab_lookup(const uint4* __restrict__ lut, float r, float g, float b
 }
 
 // integer-valued float from a 16-bit field, offset by 2^23 (differences of two such values are exact)
+#ifdef __CUDA_ARCH__
+PYSP_HD float ab_lo(uint32_t ab) { return pysp_as_float(__byte_perm(ab, 0x4B000000u, 0x7610)); }   // one PRMT each
+PYSP_HD float ab_hi(uint32_t ab) { return pysp_as_float(__byte_perm(ab, 0x4B000000u, 0x7632)); }
+#else
 PYSP_HD float ab_lo(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab & 0xFFFFu)); }
 PYSP_HD float ab_hi(uint32_t ab) { return pysp_as_float(0x4B000000u | (ab >> 16)); }
+#endif
+
+// 8-byte shared-memory pairs (one LDS.64)
+struct __attribute__((aligned(8))) F2 { float x, y; };
+struct __attribute__((aligned(8))) U2 { uint32_t x, y; };
+
+// homogeneity test of one window cell (ahd_homogeneity_cython.pyx:56-58): all ones when both the lightness and the
+// chroma test pass.  pass_ge takes the lightness difference seen from the other end of the pair (-dl <= eps).
+PYSP_HD uint32_t pass_le(float dl, float epsl, float d2, float epsc) {
+#ifdef __CUDA_ARCH__
+    uint32_t m;
+    asm("{ .reg .pred p; setp.le.f32 p, %1, %2; set.le.and.u32.f32 %0, %3, %4, p; }" : "=r"(m) : "f"(dl), "f"(epsl), "f"(d2), "f"(epsc));
+    return m;
+#else
+    return (dl <= epsl && d2 <= epsc) ? 0xFFFFFFFFu : 0u;
+#endif
+}
+PYSP_HD uint32_t pass_ge(float dl, float neg_epsl, float d2, float epsc) {
+#ifdef __CUDA_ARCH__
+    uint32_t m;
+    asm("{ .reg .pred p; setp.ge.f32 p, %1, %2; set.le.and.u32.f32 %0, %3, %4, p; }" : "=r"(m) : "f"(dl), "f"(neg_epsl), "f"(d2), "f"(epsc));
+    return m;
+#else
+    return (dl >= neg_epsl && d2 <= epsc) ? 0xFFFFFFFFu : 0u;
+#endif
+}
 
 // debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
 PYSP_HD LabQ metric_lab(const ColorParams& c, const uint4* __restrict__ lut, float r, float g, float b) {

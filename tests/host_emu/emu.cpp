@@ -72,12 +72,13 @@ static void run_chain(const DevelopPlan& plan) {
 }
 
 extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
-    // tile sizes are compile-time in the kernels; the emulation instantiates the product's K1 tile (56x28) and a small
+    // tile sizes are compile-time in the kernels; the emulation instantiates the product's K1 tile (56x30) and a small
     // one (16x8) that puts many tile seams and partial tiles into small test frames
     DevelopPlan plan;
     int rc = plan_develop(a, tw, th, tw, th, &plan, g_err, sizeof(g_err));
     if (rc) return rc;
     if (tw == 56 && th == 28) run_chain<56, 28>(plan);
+    else if (tw == 56 && th == 30) run_chain<56, 30>(plan);
     else if (tw == 16 && th == 8) run_chain<16, 8>(plan);
     else {
         snprintf(g_err, sizeof(g_err), "emu_develop: tile %dx%d not instantiated", tw, th);
