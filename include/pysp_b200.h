@@ -125,6 +125,10 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
 void pysp_timing_enable(int32_t on);
 int pysp_timing_collect(double total_ms[4], int64_t launches[4]);
 
+/* Developer hook: SM clocks per kernel phase, summed over CTAs since the last call ([kernel 0..1][phase 0..15]);
+ * all zeros unless the library was built with -DPYSP_PHASE_CLOCKS (tools/kbench.py --phases). */
+int pysp_debug_phase_clocks(uint64_t out[32]);
+
 const char* pysp_last_error(void);
 const char* pysp_version(void);
 /* Number of kernels this library has launched in this process (for bench accounting). */

@@ -271,6 +271,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     float* cand = (float*)(smem + L::OFF_CAND);
     uint16_t* cnt = (uint16_t*)(smem + L::OFF_CNT);
     float* out = (float*)(smem + L::OFF_OUT);
+    PYSP_PHASE_BEGIN();
 
     // ---------------- phase 1: directional greens and colour differences at R/B sites ---------------------
     {
@@ -297,6 +298,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
         }
     }
     PYSP_SYNC();
+    PYSP_PHASE_MARK(0, 2);
 
     // ---------------- phase 2: candidates + Lab per quad, both directions ----------------------------------
     {
@@ -400,6 +402,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
         }
     }
     PYSP_SYNC();
+    PYSP_PHASE_MARK(0, 3);
 
     // ---------------- phase 3: homogeneity counts for the tile + 1 px ---------------------------------------
     // The centre and the two neighbours along the direction always pass both tests (their distances define
@@ -500,6 +503,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     }
     before_out();
     PYSP_SYNC();
+    PYSP_PHASE_MARK(0, 4);
 
     // ---------------- phase 4: 3x3 vote, select, epilogue -> output staging tile ---------------------------
     // A count cell is 16 bits, H count in the low byte and V count in the high byte; two cells per 32-bit word.

@@ -93,13 +93,16 @@ ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant_
     };
     if (tile < p.n_tiles) fetch(tile);
     if (!p.tma_in) __syncthreads();
+    PYSP_PHASE_BEGIN();
     for (; tile < p.n_tiles; tile += gridDim.x) {
         const int tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
         const bool edge = select_tile_is_edge<K1_TW, K1_TH>(p, tile_x, tile_y);
         if (p.tma_in) { mbar_wait(bar, parity); parity ^= 1; }
+        PYSP_PHASE_MARK(0, 0);                            // wait for the raw box
         if (edge) select_phase0<K1_TW, K1_TH, true>(p, smem, tile_x, tile_y);
         else select_phase0<K1_TW, K1_TH, false>(p, smem, tile_x, tile_y);
         __syncthreads();                                  // staging consumed, quarter planes complete
+        PYSP_PHASE_MARK(0, 1);
         const int next = tile + gridDim.x;
         if (p.tma_in && next < p.n_tiles) fetch(next);
         auto before_out = [&]() { if (p.st.tma && threadIdx.x == 0) tma_store_wait_read(); };
@@ -114,10 +117,12 @@ ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant_
         }
         if (p.st.tma) fence_async_smem();                 // staging tile written by the generic proxy, read by TMA
         __syncthreads();
+        PYSP_PHASE_MARK(0, 6);
         store_tile<K1_TW, K1_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K1_TW,
                                  p.y_begin + tile_y * K1_TH);
         if (!p.tma_in && next < p.n_tiles) fetch(next);
         __syncthreads();                                  // planes free for the next tile; generic store/load done
+        PYSP_PHASE_MARK(0, 7);
     }
     if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();
 }
@@ -258,6 +263,17 @@ int pysp_timing_collect(double* total_ms, int64_t* launches) {
         cudaEventDestroy(g_tev[i].a); cudaEventDestroy(g_tev[i].b);
     }
     g_tn = 0;
+    return PYSP_OK;
+}
+
+// developer hook: per-phase SM clocks summed over CTAs (zeros unless built with -DPYSP_PHASE_CLOCKS); resets them
+int pysp_debug_phase_clocks(uint64_t out[32]) {
+    memset(out, 0, 32 * sizeof(uint64_t));
+#ifdef PYSP_PHASE_CLOCKS
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(z)) != cudaSuccess) return fail(PYSP_ERR_CUDA, "phase clocks");
+    if (cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)) != cudaSuccess) return fail(PYSP_ERR_CUDA, "phase clocks");
+#endif
     return PYSP_OK;
 }
 

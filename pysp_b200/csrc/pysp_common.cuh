@@ -36,6 +36,22 @@ __device__ __forceinline__ uint32_t pysp_as_uint(float f) { return __float_as_ui
 template <typename T> __device__ __forceinline__ T pysp_ldg(const T* p) { return __ldg(p); }
 #endif
 
+// Developer instrumentation (tools/kbench.py --phases, -DPYSP_PHASE_CLOCKS): thread 0 of every CTA accumulates the
+// SM clock between phase boundaries into g_phase_clk.  Compiled out of the product build.
+#if defined(PYSP_PHASE_CLOCKS) && !defined(PYSP_HOST_EMU)
+__device__ unsigned long long g_phase_clk[2][16];
+#define PYSP_PHASE_BEGIN() long long ph_t_ = clock64()
+#define PYSP_PHASE_MARK(k, i)                                                          \
+    if (threadIdx.x == 0) {                                                            \
+        long long n_ = clock64();                                                      \
+        atomicAdd(&g_phase_clk[k][i], (unsigned long long)(n_ - ph_t_));               \
+        ph_t_ = n_;                                                                    \
+    }
+#else
+#define PYSP_PHASE_BEGIN() ((void)0)
+#define PYSP_PHASE_MARK(k, i) ((void)0)
+#endif
+
 namespace pysp {
 
 // ---- constants of the reference algorithm ---------------------------------------------------------

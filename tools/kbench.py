@@ -44,11 +44,19 @@ def one(stages, reps):
     n = (ctypes.c_int64 * 4)()
     _capi.check(lib.pysp_timing_collect(tot, n))
     lib.pysp_timing_enable(0)
+    clk = (ctypes.c_uint64 * 32)()
+    lib.pysp_debug_phase_clocks.argtypes = [ctypes.c_void_p]
+    lib.pysp_debug_phase_clocks(clk)
     run(frames[0])
     torch.cuda.synchronize()
     h = hashlib.sha1(out.cpu().numpy().tobytes()).hexdigest()[:16]
     res = {"lib": os.path.basename(_capi.LIB_PATH), "stages": stages,
            "k1_ms": tot[0] / max(n[0], 1), "k2_ms": tot[1] / max(n[1], 1), "sha1": h}
+    if any(clk):
+        for k in range(2):
+            t = sum(clk[16 * k:16 * k + 16])
+            if t:
+                res["k%d_phase_share" % (k + 1)] = [round(clk[16 * k + i] / t, 4) for i in range(16)]
     print(json.dumps(res))
 
 
