@@ -118,6 +118,40 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
                         float* out, int64_t out_pitch_bytes, int32_t* count, int64_t count_pitch_bytes,
                         void* stream);
 
+/* ---- steps either side of the develop path ------------------------------------------------ */
+
+/* Bytes of device workspace pysp_flat_frame_correction / pysp_bayer_plane_means need for an H x W mosaic. */
+int64_t pysp_flat_workspace_bytes(int32_t height, int32_t width);
+
+/* np.mean of the four CFA planes R, G1, B, G2 of a float32 mosaic (raw_correction.py:45), bit-identical to NumPy:
+ * the float32 pairwise summation tree of NumPy is evaluated in its own order on the device.  means: 4 floats (device). */
+int pysp_bayer_plane_means(const float* mosaic, int64_t pitch_bytes, int32_t height, int32_t width, float* means,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* flat_frame_correction (raw_correction.py:25-63): per CFA plane out = (sensor * mean(flat)) / flat; +inf -> largest
+ * finite quotient of the plane, negative -> 0, optional clamp at 1; a plane whose quotients are all infinite is
+ * copied unchanged.  `out` may alias `sensor`. */
+int pysp_flat_frame_correction(const float* sensor, int64_t sensor_pitch_bytes, const float* flat, int64_t flat_pitch_bytes,
+                               float* out, int64_t out_pitch_bytes, int32_t height, int32_t width, int32_t clamp_high,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* find_erroneous_pixels_threshold (raw_bad_pixel_corr.py:30-65): masks[4][H/2][W/2] bytes (planes R, G1, B, G2), 1 where
+ * (value - min_delta) exceeds more than min_neighbour_count of the eight same-colour neighbours (reflected border). */
+int pysp_find_hot_pixels_threshold(const float* sensor, int64_t pitch_bytes, int32_t height, int32_t width, float min_delta,
+                                   int32_t min_neighbour_count, uint8_t* masks, void* stream);
+
+/* fuse_exposures_from_debayer (raw_hdr.py:7-83): n demosaiced exposures (float32 [n_pixels][3], white balance applied)
+ * -> linear sRGB float32 (+ optional int32 [n_pixels][3] contribution count).  Per exposure, in list order: wb_undo
+ * (float64 division, base_types/image_base.py:52-60), saturation weight x bias[i], wb_apply, accumulation x
+ * ev_offset[i]; where the weights sum to zero the brightest exposure x offset_max (float64) is used; then the camera
+ * -> linear-sRGB matrix without clipping.  ev_offset[i] = float32(2**(ev_i - target)), bias[i] =
+ * float32(1.6**(-0.1 * 2**(ev_i - target))), brightest = last i whose offset equals offset_max.  With write_back the
+ * exposures are left as the reference leaves them (after its wb_undo/wb_apply round trip). */
+int pysp_fuse_exposures_from_debayer(float* const* images, int32_t n, int64_t n_pixels, const float wb[3], float max_wb,
+                                     const int32_t* wb_normalized, const float* ev_offset, const float* bias,
+                                     int32_t brightest, double offset_max, const double m[9], float* out, int32_t* count,
+                                     int32_t write_back, void* stream);
+
 /* Bench instrumentation (no reference counterpart): when enabled, pysp_develop brackets each kernel launch
  * with CUDA events on the launching stream; collect() synchronises them and returns, per kernel slot
  * (0 = ahd_select_kernel, 1 = median_stage_kernel; 4 slots), the summed device milliseconds and launch

@@ -7,7 +7,9 @@ Drop-in names (reference module in brackets):
     bayer_normalize                                                            [normalization.py]
     debayer_ahd, debayer_eag                                                   [debayer/__init__.py]
     cam_to_lin_srgb, cam_to_rgb_norm, clip_rgb, lin_srgb_to_srgb               [colorize/transform.py]
-    fuse_exposures_to_raw                                                      [raw_hdr.py]
+    fuse_exposures_to_raw, fuse_exposures_from_debayer                         [raw_hdr.py]
+    flat_frame_correction, dark_frame_subtraction, bias_frame_subtraction      [raw_correction.py]
+    find_erroneous_pixels_threshold                                            [raw_bad_pixel_corr.py]
 The compute path is hand-written CUDA (sm_100a) behind a C ABI (include/pysp_b200.h); there is no CPU
 fallback -- importing is cheap, but any compute call needs libpysp_b200.so and a CUDA device.
 """
@@ -24,7 +26,10 @@ def __getattr__(name):
         "bayer_normalize": ".normalization", "debayer_ahd": ".debayer", "debayer_eag": ".debayer",
         "cam_to_lin_srgb": ".colorize.transform", "cam_to_rgb_norm": ".colorize.transform",
         "clip_rgb": ".colorize.transform", "lin_srgb_to_srgb": ".colorize.transform",
-        "fuse_exposures_to_raw": ".raw_hdr", "CameraWhiteBalance": ".wb_cct.cam_wb",
+        "fuse_exposures_to_raw": ".raw_hdr", "fuse_exposures_from_debayer": ".raw_hdr",
+        "flat_frame_correction": ".raw_correction", "dark_frame_subtraction": ".raw_correction",
+        "bias_frame_subtraction": ".raw_correction", "find_erroneous_pixels_threshold": ".raw_bad_pixel_corr",
+        "CameraWhiteBalance": ".wb_cct.cam_wb",
         "MatXyzToCamera": ".wb_cct.helpers_cam_mat",
     }
     if name in table:

@@ -70,6 +70,22 @@ def lib():
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_void_p,
                                       C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     L.pysp_fuse_exposures.restype = C.c_int
+    L.pysp_flat_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.pysp_flat_workspace_bytes.restype = C.c_int64
+    L.pysp_bayer_plane_means.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p]
+    L.pysp_bayer_plane_means.restype = C.c_int
+    L.pysp_flat_frame_correction.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    L.pysp_flat_frame_correction.restype = C.c_int
+    L.pysp_find_hot_pixels_threshold.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                                 C.c_void_p, C.c_void_p]
+    L.pysp_find_hot_pixels_threshold.restype = C.c_int
+    L.pysp_fuse_exposures_from_debayer.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.POINTER(C.c_float),
+                                                   C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                                   C.POINTER(C.c_float), C.c_int32, C.c_double, C.POINTER(C.c_double),
+                                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.pysp_fuse_exposures_from_debayer.restype = C.c_int
     L.pysp_timing_enable.argtypes = [C.c_int32]
     L.pysp_timing_enable.restype = None
     L.pysp_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]

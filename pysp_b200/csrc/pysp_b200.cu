@@ -7,14 +7,19 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "../../include/pysp_b200.h"
 #include "ahd_select.cuh"
 #include "eag.cuh"
 #include "median_stage.cuh"
 #include "pointwise.cuh"
+#include "prepost.cuh"
 #include "develop_plan.h"
 
 namespace pysp {
@@ -484,6 +489,196 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
     p.out = out; p.out_pitch = out_pitch; p.count = count; p.count_pitch = count_pitch;
     fuse_kernel<<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("fuse_kernel");
+}
+
+}  // extern "C"
+
+// ---- NumPy-ordered float32 plane sums (prepost.cuh) -----------------------------------------------------------------
+namespace {
+struct PlaneSumPlan {            // host layout of NumPy's pairwise-sum tree for n elements
+    std::vector<int> leaf_off, leaf_len, node_l, node_r, group_start;
+};
+
+int build_sum_tree(long long off, long long n, PlaneSumPlan& pl, std::vector<int>& height, std::vector<int>& h_of_val) {
+    // returns the value index of the subtree's result: leaves are (index), nodes are encoded as -(k+1) until renumbered
+    if (n <= 128) {
+        pl.leaf_off.push_back((int)off); pl.leaf_len.push_back((int)n);
+        return (int)pl.leaf_off.size() - 1;
+    }
+    long long n2 = n / 2;
+    n2 -= n2 % 8;
+    const int l = build_sum_tree(off, n2, pl, height, h_of_val);
+    const int r = build_sum_tree(off + n2, n - n2, pl, height, h_of_val);
+    auto h = [&](int v) { return v >= 0 ? 0 : height[-v - 1]; };
+    pl.node_l.push_back(l); pl.node_r.push_back(r);
+    height.push_back(std::max(h(l), h(r)) + 1);
+    return -(int)pl.node_l.size();
+}
+
+std::shared_ptr<const PlaneSumPlan> plane_sum_plan(long long n) {
+    static std::mutex mu;
+    static std::map<long long, std::shared_ptr<const PlaneSumPlan>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(n);
+    if (it != cache.end()) return it->second;
+    auto pl = std::make_shared<PlaneSumPlan>();
+    std::vector<int> height, unused;
+    build_sum_tree(0, n, *pl, height, unused);
+    const int nn = (int)pl->node_l.size(), nl = (int)pl->leaf_off.size();
+    std::vector<int> order(nn), rank(nn);
+    for (int k = 0; k < nn; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return height[a] < height[b]; });
+    for (int k = 0; k < nn; ++k) rank[order[k]] = k;
+    std::vector<int> nl_(nn), nr_(nn);
+    auto val = [&](int v) { return v >= 0 ? v : nl + rank[-v - 1]; };
+    for (int k = 0; k < nn; ++k) { nl_[k] = val(pl->node_l[order[k]]); nr_[k] = val(pl->node_r[order[k]]); }
+    pl->node_l.swap(nl_); pl->node_r.swap(nr_);
+    pl->group_start.push_back(0);
+    for (int k = 1; k <= nn; ++k)
+        if (k == nn || height[order[k]] != height[order[k - 1]]) pl->group_start.push_back(k);
+    if (cache.size() > 64) cache.clear();
+    cache[n] = pl;
+    return pl;
+}
+
+long long align16(long long v) { return (v + 15) / 16 * 16; }
+
+struct FlatWorkspace { long long off_leaf_off, off_leaf_len, off_node_l, off_node_r, off_group, off_val, off_mean, off_stat, total; };
+
+FlatWorkspace flat_workspace_layout(const PlaneSumPlan& pl) {
+    FlatWorkspace w;
+    long long o = 0;
+    const long long nl = (long long)pl.leaf_off.size(), nn = (long long)pl.node_l.size();
+    w.off_leaf_off = o; o = align16(o + 4 * nl);
+    w.off_leaf_len = o; o = align16(o + 4 * nl);
+    w.off_node_l = o; o = align16(o + 4 * nn);
+    w.off_node_r = o; o = align16(o + 4 * nn);
+    w.off_group = o; o = align16(o + 4 * (long long)pl.group_start.size());
+    w.off_val = o; o = align16(o + 4 * 4 * (nl + nn));
+    w.off_mean = o; o = align16(o + 16);
+    w.off_stat = o; o = align16(o + 32);
+    w.total = o;
+    return w;
+}
+
+// uploads the tree tables into the workspace and launches the two summation kernels; mean[4] lands at ws + off_mean
+int launch_plane_means(const float* mosaic, long long pitch, int H, int W, char* ws, const PlaneSumPlan& pl, const FlatWorkspace& lay,
+                       PlaneSumTables* tables, cudaStream_t stream) {
+    const int nl = (int)pl.leaf_off.size(), nn = (int)pl.node_l.size(), ng = (int)pl.group_start.size() - 1;
+    cudaError_t e = cudaMemcpyAsync(ws + lay.off_leaf_off, pl.leaf_off.data(), 4LL * nl, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + lay.off_leaf_len, pl.leaf_len.data(), 4LL * nl, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && nn) e = cudaMemcpyAsync(ws + lay.off_node_l, pl.node_l.data(), 4LL * nn, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && nn) e = cudaMemcpyAsync(ws + lay.off_node_r, pl.node_r.data(), 4LL * nn, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + lay.off_group, pl.group_start.data(), 4LL * (ng + 1), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "plane means: table upload: %s", cudaGetErrorString(e));
+    PlaneSumTables t;
+    t.leaf_off = (const int*)(ws + lay.off_leaf_off); t.leaf_len = (const int*)(ws + lay.off_leaf_len);
+    t.node_l = (const int*)(ws + lay.off_node_l); t.node_r = (const int*)(ws + lay.off_node_r);
+    t.group_start = (const int*)(ws + lay.off_group);
+    t.n_leaves = nl; t.n_nodes = nn; t.n_groups = ng;
+    t.val = (float*)(ws + lay.off_val);
+    *tables = t;
+    leaf_sum_kernel<<<grid_for(4LL * nl, 128), 128, 0, stream>>>(mosaic, pitch, W, t);
+    int rc = check_launch("leaf_sum_kernel");
+    if (rc) return rc;
+    const long long n = (long long)(H / 2) * (W / 2);
+    tree_sum_kernel<<<4, 1024, 0, stream>>>(t, (float)n, (float*)(ws + lay.off_mean));
+    return check_launch("tree_sum_kernel");
+}
+}  // namespace
+
+extern "C" {
+
+int64_t pysp_flat_workspace_bytes(int32_t H, int32_t W) {
+    if (H < 2 || W < 2 || (H & 1) || (W & 1)) return 0;
+    auto pl = plane_sum_plan((long long)(H / 2) * (W / 2));
+    return flat_workspace_layout(*pl).total;
+}
+
+int pysp_bayer_plane_means(const float* mosaic, int64_t pitch, int32_t H, int32_t W, float* means, void* workspace,
+                           int64_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!mosaic || !means || !workspace) return fail(PYSP_ERR_INVALID, "pysp_bayer_plane_means: null pointer");
+    if (H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(PYSP_ERR_INVALID, "pysp_bayer_plane_means: dims must be even");
+    if (pitch < 4LL * W) return fail(PYSP_ERR_INVALID, "pysp_bayer_plane_means: bad pitch");
+    int rc = ensure_device();
+    if (rc) return rc;
+    auto pl = plane_sum_plan((long long)(H / 2) * (W / 2));
+    const FlatWorkspace lay = flat_workspace_layout(*pl);
+    if (workspace_bytes < lay.total) return fail(PYSP_ERR_INVALID, "pysp_bayer_plane_means: workspace too small (%lld < %lld)", (long long)workspace_bytes, lay.total);
+    PlaneSumTables t;
+    rc = launch_plane_means(mosaic, pitch, H, W, (char*)workspace, *pl, lay, &t, stream);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(means, (char*)workspace + lay.off_mean, 16, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "pysp_bayer_plane_means: %s", cudaGetErrorString(e));
+    return PYSP_OK;
+}
+
+int pysp_flat_frame_correction(const float* sensor, int64_t sensor_pitch, const float* flat, int64_t flat_pitch, float* out,
+                               int64_t out_pitch, int32_t H, int32_t W, int32_t clamp_high, void* workspace,
+                               int64_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sensor || !flat || !out || !workspace) return fail(PYSP_ERR_INVALID, "pysp_flat_frame_correction: null pointer");
+    if (H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(PYSP_ERR_INVALID, "pysp_flat_frame_correction: dims must be even");
+    if (sensor_pitch < 4LL * W || flat_pitch < 4LL * W || out_pitch < 4LL * W) return fail(PYSP_ERR_INVALID, "pysp_flat_frame_correction: bad pitch");
+    int rc = ensure_device();
+    if (rc) return rc;
+    auto pl = plane_sum_plan((long long)(H / 2) * (W / 2));
+    const FlatWorkspace lay = flat_workspace_layout(*pl);
+    if (workspace_bytes < lay.total) return fail(PYSP_ERR_INVALID, "pysp_flat_frame_correction: workspace too small (%lld < %lld)", (long long)workspace_bytes, lay.total);
+    char* ws = (char*)workspace;
+    FlatParams p;
+    rc = launch_plane_means(flat, flat_pitch, H, W, ws, *pl, lay, &p.t, stream);
+    if (rc) return rc;
+    const int stat0[8] = {PYSP_KEY_NONE, 0, PYSP_KEY_NONE, 0, PYSP_KEY_NONE, 0, PYSP_KEY_NONE, 0};
+    cudaError_t e = cudaMemcpyAsync(ws + lay.off_stat, stat0, sizeof(stat0), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "pysp_flat_frame_correction: %s", cudaGetErrorString(e));
+    p.sensor = sensor; p.sensor_pitch = sensor_pitch; p.flat = flat; p.flat_pitch = flat_pitch; p.out = out; p.out_pitch = out_pitch;
+    p.H = H; p.W = W; p.clamp_high = clamp_high; p.n_f32 = (float)((long long)(H / 2) * (W / 2));
+    p.mean = (float*)(ws + lay.off_mean); p.stat = (int*)(ws + lay.off_stat);
+    flat_stats_kernel<<<grid_for((long long)H * W, 256), 256, 0, stream>>>(p);
+    rc = check_launch("flat_stats_kernel");
+    if (rc) return rc;
+    flat_apply_kernel<<<grid_for((long long)H * W, 256), 256, 0, stream>>>(p);
+    return check_launch("flat_apply_kernel");
+}
+
+int pysp_find_hot_pixels_threshold(const float* sensor, int64_t pitch, int32_t H, int32_t W, float min_delta,
+                                   int32_t min_neighbour_count, uint8_t* masks, void* stream) {
+    if (!sensor || !masks) return fail(PYSP_ERR_INVALID, "pysp_find_hot_pixels_threshold: null pointer");
+    if (H < 4 || W < 4 || (H & 1) || (W & 1)) return fail(PYSP_ERR_INVALID, "pysp_find_hot_pixels_threshold: dims must be even and >= 4");
+    if (pitch < 4LL * W) return fail(PYSP_ERR_INVALID, "pysp_find_hot_pixels_threshold: bad pitch");
+    int rc = ensure_device();
+    if (rc) return rc;
+    HotParams p;
+    p.sensor = sensor; p.pitch = pitch; p.H = H; p.W = W; p.min_delta = min_delta; p.min_count = min_neighbour_count; p.masks = masks;
+    hot_pixel_kernel<<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("hot_pixel_kernel");
+}
+
+int pysp_fuse_exposures_from_debayer(float* const* images, int32_t n, int64_t n_pixels, const float wb[3], float max_wb,
+                                     const int32_t* wb_normalized, const float* ev_offset, const float* bias, int32_t brightest,
+                                     double offset_max, const double m[9], float* out, int32_t* count, int32_t write_back,
+                                     void* stream) {
+    if (!images || !wb || !ev_offset || !bias || !m || !out) return fail(PYSP_ERR_INVALID, "pysp_fuse_exposures_from_debayer: null pointer");
+    if (n < 1 || n > PYSP_MAX_EXPOSURES) return fail(PYSP_ERR_INVALID, "pysp_fuse_exposures_from_debayer: 1..%d exposures", PYSP_MAX_EXPOSURES);
+    if (brightest < 0 || brightest >= n || n_pixels < 0) return fail(PYSP_ERR_INVALID, "pysp_fuse_exposures_from_debayer: bad argument");
+    if (n_pixels == 0) return PYSP_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    FuseCamParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < n; ++i) {
+        if (!images[i]) return fail(PYSP_ERR_INVALID, "pysp_fuse_exposures_from_debayer: null exposure %d", i);
+        p.img[i] = images[i]; p.ev_off[i] = ev_offset[i]; p.bias[i] = bias[i];
+        p.normalized[i] = wb_normalized ? wb_normalized[i] : 0;
+    }
+    p.n = n; p.n_px = n_pixels; p.brightest = brightest; p.off_max = offset_max; p.out = out; p.count = count; p.write_back = write_back;
+    p.max_wb = max_wb;
+    for (int c = 0; c < 3; ++c) p.wb[c] = wb[c];
+    for (int i = 0; i < 9; ++i) p.m[i] = m[i];
+    fuse_cam_kernel<<<grid_for(n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("fuse_cam_kernel");
 }
 
 }  // extern "C"

@@ -204,5 +204,88 @@ def fuse_exposures(brackets, ev_offsets, bias, brightest, want_count=True, strea
     return out, cnt
 
 
+def _f32_2d(t, what):
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2:
+        raise ValueError("%s: float32 CUDA tensor [H,W] expected" % what)
+    if t.shape[0] % 2 or t.shape[1] % 2:
+        raise ValueError("%s: mosaic must have even dimensions" % what)
+    return t if t.stride(1) == 1 else t.contiguous()
+
+
+def bayer_plane_means(mosaic, stream=None):
+    """np.mean of the R, G1, B, G2 planes of a float32 mosaic, bit-identical to NumPy (4 floats on the device)."""
+    require_cuda()
+    L = _capi.lib()
+    mosaic = _f32_2d(mosaic, "bayer_plane_means")
+    H, W = mosaic.shape
+    with torch.cuda.device(mosaic.device):
+        nws = int(L.pysp_flat_workspace_bytes(H, W))
+        ws = torch.empty(nws, dtype=torch.uint8, device=mosaic.device)
+        out = torch.empty(4, dtype=torch.float32, device=mosaic.device)
+        _capi.check(L.pysp_bayer_plane_means(mosaic.data_ptr(), mosaic.stride(0) * 4, H, W, out.data_ptr(), ws.data_ptr(), nws,
+                                             _stream_ptr(stream)))
+    return out
+
+
+def flat_frame_correction(sensor, flat, clamp_high=False, stream=None):
+    """raw_correction.py:25-63 on the device; returns the corrected float32 mosaic."""
+    require_cuda()
+    L = _capi.lib()
+    sensor = _f32_2d(sensor, "flat_frame_correction")
+    flat = _f32_2d(flat, "flat_frame_correction")
+    if flat.shape != sensor.shape or flat.device != sensor.device:
+        raise ValueError("flat_frame_correction: image and flat field must have the same shape and device")
+    H, W = sensor.shape
+    with torch.cuda.device(sensor.device):
+        nws = int(L.pysp_flat_workspace_bytes(H, W))
+        ws = torch.empty(nws, dtype=torch.uint8, device=sensor.device)
+        out = torch.empty_like(sensor)
+        _capi.check(L.pysp_flat_frame_correction(sensor.data_ptr(), sensor.stride(0) * 4, flat.data_ptr(), flat.stride(0) * 4,
+                                                 out.data_ptr(), out.stride(0) * 4, H, W, int(bool(clamp_high)), ws.data_ptr(),
+                                                 nws, _stream_ptr(stream)))
+    return out
+
+
+def find_hot_pixels_threshold(sensor, min_delta, min_neighbour_count, stream=None):
+    """raw_bad_pixel_corr.py:30-65 on the device; returns a bool tensor [4, H/2, W/2] (planes R, G1, B, G2)."""
+    require_cuda()
+    L = _capi.lib()
+    sensor = _f32_2d(sensor, "find_hot_pixels_threshold")
+    H, W = sensor.shape
+    with torch.cuda.device(sensor.device):
+        masks = torch.empty((4, H // 2, W // 2), dtype=torch.uint8, device=sensor.device)
+        _capi.check(L.pysp_find_hot_pixels_threshold(sensor.data_ptr(), sensor.stride(0) * 4, H, W, float(min_delta),
+                                                     int(min_neighbour_count), masks.data_ptr(), _stream_ptr(stream)))
+    return masks.view(torch.bool)
+
+
+def fuse_exposures_from_debayer(images, wb, max_wb, normalized, ev_offsets, bias, brightest, offset_max, matrix,
+                                write_back=True, want_count=True, stream=None):
+    """raw_hdr.py:47-81 on the device.  images: float32 CUDA tensors [H,W,3] (contiguous; rewritten when write_back)."""
+    require_cuda()
+    L = _capi.lib()
+    n = len(images)
+    dev = images[0].device
+    for t in images:
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 3 or t.shape != images[0].shape or t.shape[2] != 3 \
+                or not t.is_contiguous() or t.device != dev:
+            raise ValueError("fuse_exposures_from_debayer: contiguous float32 CUDA tensors [H,W,3] of one shape expected")
+    npx = images[0].shape[0] * images[0].shape[1]
+    out = torch.empty_like(images[0])
+    cnt = torch.empty(images[0].shape, dtype=torch.int32, device=dev) if want_count else None
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in images])
+    wb3 = (C.c_float * 3)(*[float(v) for v in wb[:3]])
+    norm = (C.c_int32 * n)(*[int(bool(v)) for v in normalized])
+    evo = (C.c_float * n)(*[float(v) for v in ev_offsets])
+    bia = (C.c_float * n)(*[float(v) for v in bias])
+    m = (C.c_double * 9)(*[float(v) for row in np.asarray(matrix, dtype=np.float64) for v in row])
+    with torch.cuda.device(dev):
+        _capi.check(L.pysp_fuse_exposures_from_debayer(ptrs, n, npx, wb3, float(max_wb), norm, evo, bia, int(brightest),
+                                                       float(offset_max), m, out.data_ptr(),
+                                                       cnt.data_ptr() if cnt is not None else None, int(bool(write_back)),
+                                                       _stream_ptr(stream)))
+    return out, cnt
+
+
 def kernel_launches():
     return int(_capi.lib().pysp_kernel_launches())

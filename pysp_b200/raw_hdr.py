@@ -1,9 +1,11 @@
-"""Raw-space HDR fusion -- reference: raw_hdr.py:85-158 (`fuse_exposures_to_raw`)."""
+"""HDR fusion -- reference: raw_hdr.py:85-158 (`fuse_exposures_to_raw`, raw space) and raw_hdr.py:7-83
+(`fuse_exposures_from_debayer`, camera space)."""
 import numpy as np
 import torch
 
 from . import engine
 from ._arrays import as_cuda, give_back, is_numpy
+from .colour import cam_to_rgb_matrix
 from .image import RawRggbBayerData
 
 
@@ -47,3 +49,47 @@ def fuse_exposures_to_raw(in_exposures, target_ev=None):
                            in_exposures[0].source_pattern)
     hdr.set_hdr(True)
     return hdr, give_back(count, want_np)
+
+
+def fuse_exposures_from_debayer(in_exposures, target_ev=None):
+    """Fuse demosaiced exposures to linear sRGB HDR (raw_hdr.py:7-83).  Returns (linear sRGB image, int32 buffer of
+    contributions per pixel and channel), or None when no exposure is valid.  As in the reference, every valid
+    exposure goes through wb_undo()/wb_apply() and keeps the (re-rounded) image that leaves."""
+    valid = [e for e in in_exposures if e.is_valid()]
+    if len(valid) == 0:
+        return None
+    if len(valid) > 16:
+        raise ValueError("fuse_exposures_from_debayer: at most 16 exposures")
+    if target_ev is None:
+        target_ev = 0
+        for e in valid:
+            target_ev += e.current_ev
+        target_ev /= len(valid)
+    else:
+        assert target_ev > 0
+    offsets = [2 ** (e.current_ev - target_ev) for e in valid]
+    off_max = np.max(offsets)
+    brightest = max(i for i, o in enumerate(offsets) if o == off_max)
+    bias = [np.float32(1.6 ** (-0.1 * o)) for o in offsets]
+    want_np = is_numpy(in_exposures[0].image)
+    wb = np.asarray(valid[0]._wb_coeff, dtype=np.float32)
+    for e in valid:
+        if not np.array_equal(np.asarray(e._wb_coeff, dtype=np.float32), wb):
+            raise ValueError("fuse_exposures_from_debayer: exposures must share their white-balance coefficients")
+    imgs, dev = [], None
+    for e in valid:
+        t = as_cuda(e.image, torch.float32, device=dev)
+        dev = t.device
+        if not e._wb_applied:                       # wb_undo() is a no-op then; wb_apply() still multiplies
+            raise ValueError("fuse_exposures_from_debayer: exposures are expected with white balance applied")
+        t = t.contiguous()
+        if isinstance(e.image, torch.Tensor) and t.data_ptr() == e.image.data_ptr():
+            t = t.clone()                           # the reference assigns new arrays; the caller's tensor is not rewritten
+        imgs.append(t)
+    m = cam_to_rgb_matrix(in_exposures[0].mat_xyz)
+    lin, cnt = engine.fuse_exposures_from_debayer(imgs, wb[:3], float(max(wb)), [e._wb_normalized for e in valid],
+                                                  [np.float32(o) for o in offsets], bias, brightest, float(off_max), m)
+    for e, t in zip(valid, imgs):
+        e.image = give_back(t, is_numpy(e.image))
+        e._wb_normalized = False
+    return give_back(lin, want_np), give_back(cnt, want_np)
