@@ -32,18 +32,46 @@ struct FuseParams {           // raw_hdr.py:108-148
 };
 
 #ifndef PYSP_HOST_EMU
+// Row-wise work split shared by the point-wise kernels: a work item is `VEC` consecutive elements of one row, so that
+// every access is a 16-byte vector and the only division is a 32-bit one per item.
+struct RowItems {
+    int per_row; long long total;
+    __device__ RowItems(int rows, int cols, int vec) : per_row((cols + vec - 1) / vec), total((long long)rows * ((cols + vec - 1) / vec)) {}
+};
+#define PYSP_ROW_ITEMS(ri, y, c)                                                                              \
+    for (long long it_ = blockIdx.x * (long long)blockDim.x + threadIdx.x, y = 0, c = 0;                      \
+         it_ < (ri).total && ((y = it_ / (ri).per_row), (c = it_ - y * (ri).per_row), true);                  \
+         it_ += (long long)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ float norm_site(float raw, float black, float white) {
+    return fminf(fmaxf(raw - black, 0.0f), white) / white;            // normalization.py:20-23
+}
+
 __global__ void __launch_bounds__(256) normalize_kernel(NormalizeParams p) {
-    // one thread = two horizontally adjacent photosites
-    long long n = (long long)p.H * (p.W >> 1);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int y = (int)(i / (p.W >> 1)), x = (int)(i - (long long)y * (p.W >> 1)) * 2;
-        const uint16_t* src = (const uint16_t*)((const char*)p.in + y * p.in_pitch) + x;
-        float* dst = (float*)((char*)p.out + y * p.out_pitch) + x;
-        int pos = (y & 1) << 1;
-        float a = (float)src[0], b = (float)src[1];
-        a = fminf(fmaxf(a - p.black[pos], 0.0f), p.white[pos]) / p.white[pos];
-        b = fminf(fmaxf(b - p.black[pos + 1], 0.0f), p.white[pos + 1]) / p.white[pos + 1];
-        dst[0] = a; dst[1] = b;
+    // one item = eight photosites of a row: one 16-byte load, two 16-byte stores
+    const RowItems ri(p.H, p.W, 8);
+    const bool vec = (p.W % 8 == 0) && (p.in_pitch % 16 == 0) && (p.out_pitch % 16 == 0) &&
+                     (((size_t)p.in | (size_t)p.out) % 16 == 0);
+    PYSP_ROW_ITEMS(ri, y, c) {
+        const int x0 = (int)c * 8;
+        const uint16_t* src = (const uint16_t*)((const char*)p.in + y * p.in_pitch) + x0;
+        float* dst = (float*)((char*)p.out + y * p.out_pitch) + x0;
+        const int pos = ((int)y & 1) << 1;
+        const float b0 = p.black[pos], b1 = p.black[pos + 1], w0 = p.white[pos], w1 = p.white[pos + 1];
+        if (vec) {
+            const uint4 v = *(const uint4*)src;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[2 * k] = norm_site((float)(w[k] & 0xFFFFu), b0, w0);
+                o[2 * k + 1] = norm_site((float)(w[k] >> 16), b1, w1);
+            }
+            *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+            *(float4*)(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+            for (int k = 0; k < 8 && x0 + k < p.W; ++k) dst[k] = norm_site((float)src[k], (k & 1) ? b1 : b0, (k & 1) ? w1 : w0);
+        }
     }
 }
 
@@ -65,28 +93,66 @@ __global__ void __launch_bounds__(256) matrix_kernel(MatrixParams p) {
 }
 
 __global__ void __launch_bounds__(256) gamma_kernel(GammaParams p) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x)
+    const long long n4 = (((size_t)p.in | (size_t)p.out) % 16 == 0) ? p.n / 4 : 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = ((const float4*)p.in)[i];
+        ((float4*)p.out)[i] = make_float4(srgb_gamma(v.x), srgb_gamma(v.y), srgb_gamma(v.z), srgb_gamma(v.w));
+    }
+    for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x)
         p.out[i] = srgb_gamma(p.in[i]);
 }
 
 __global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
-    long long n = (long long)p.H * p.W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int y = (int)(i / p.W), x = (int)(i - (long long)y * p.W);
-        int ch = (y & 1) + (x & 1);
-        float sum_w = 0.0f, sum_p = 0.0f, bright = 0.0f;
-        int cnt = 0;
-        for (int k = 0; k < p.n; ++k) {          // strictly in list order (raw_hdr.py:135-141)
-            float v = *((const float*)((const char*)p.in[k] + y * p.in_pitch) + x);
-            float w = (0.5f - fabsf(v - 0.5f)) * p.bias[k][ch];
-            sum_w = sum_w + w;
-            sum_p = sum_p + ((v * w) * p.ev_off[k]);
-            cnt += w > 0.0f ? 1 : 0;
-            if (k == p.brightest) bright = v * p.ev_off[k];
+    // one item = four photosites of a row (two CFA sites, alternating)
+    const RowItems ri(p.H, p.W, 4);
+    bool vec = (p.W % 4 == 0) && (p.in_pitch % 16 == 0) && (p.out_pitch % 16 == 0) && ((size_t)p.out % 16 == 0) &&
+               (!p.count || (p.count_pitch % 16 == 0 && (size_t)p.count % 16 == 0));
+    for (int k = 0; k < p.n; ++k) vec = vec && ((size_t)p.in[k] % 16 == 0);
+    PYSP_ROW_ITEMS(ri, y, c) {
+        const int x0 = (int)c * 4;
+        const int ch0 = (int)y & 1;                                    // channel of even columns: R (0) or G (1); odd: +1
+        float sum_w[4] = {0, 0, 0, 0}, sum_p[4] = {0, 0, 0, 0}, bright[4] = {0, 0, 0, 0};
+        int cnt[4] = {0, 0, 0, 0};
+        const int nv = vec ? 4 : min(4, p.W - x0);
+        for (int k0 = 0; k0 < p.n; k0 += 4) {    // four brackets' loads in flight, accumulation strictly in list order
+            float v[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k0 + kk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[kk][j] = 0.0f;
+                if (k < p.n) {
+                    const float* src = (const float*)((const char*)p.in[k] + y * p.in_pitch) + x0;
+                    if (vec) { const float4 t = *(const float4*)src; v[kk][0] = t.x; v[kk][1] = t.y; v[kk][2] = t.z; v[kk][3] = t.w; }
+                    else for (int j = 0; j < nv; ++j) v[kk][j] = src[j];
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k0 + kk;
+                if (k >= p.n) break;
+                const float bias0 = p.bias[k][ch0], bias1 = p.bias[k][ch0 + 1], ev = p.ev_off[k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float w = (0.5f - fabsf(v[kk][j] - 0.5f)) * ((j & 1) ? bias1 : bias0);     // raw_hdr.py:135-141
+                    sum_w[j] = sum_w[j] + w;
+                    sum_p[j] = sum_p[j] + ((v[kk][j] * w) * ev);
+                    cnt[j] += w > 0.0f ? 1 : 0;
+                    if (k == p.brightest) bright[j] = v[kk][j] * ev;
+                }
+            }
         }
-        float q = sum_p / sum_w;
-        *((float*)((char*)p.out + y * p.out_pitch) + x) = (sum_w == 0.0f) ? bright : q;
-        if (p.count) *((int32_t*)((char*)p.count + y * p.count_pitch) + x) = cnt;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float q = sum_p[j] / sum_w[j]; o[j] = (sum_w[j] == 0.0f) ? bright[j] : q; }
+        float* dst = (float*)((char*)p.out + y * p.out_pitch) + x0;
+        int32_t* dc = p.count ? (int32_t*)((char*)p.count + y * p.count_pitch) + x0 : nullptr;
+        if (vec) {
+            *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
+            if (dc) *(int4*)dc = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        } else {
+            for (int j = 0; j < nv; ++j) { dst[j] = o[j]; if (dc) dc[j] = cnt[j]; }
+        }
     }
 }
 #endif

@@ -497,6 +497,9 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
 namespace {
 struct PlaneSumPlan {            // host layout of NumPy's pairwise-sum tree for n elements
     std::vector<int> leaf_off, leaf_len, node_l, node_r, group_start;
+    // device copies of the five tables, one allocation per device (internal, cached; never freed before exit)
+    mutable std::mutex dev_mu;
+    mutable std::map<int, int*> dev_tables;
 };
 
 int build_sum_tree(long long off, long long n, PlaneSumPlan& pl, std::vector<int>& height, std::vector<int>& h_of_val) {
@@ -536,24 +539,18 @@ std::shared_ptr<const PlaneSumPlan> plane_sum_plan(long long n) {
     pl->group_start.push_back(0);
     for (int k = 1; k <= nn; ++k)
         if (k == nn || height[order[k]] != height[order[k - 1]]) pl->group_start.push_back(k);
-    if (cache.size() > 64) cache.clear();
     cache[n] = pl;
     return pl;
 }
 
 long long align16(long long v) { return (v + 15) / 16 * 16; }
 
-struct FlatWorkspace { long long off_leaf_off, off_leaf_len, off_node_l, off_node_r, off_group, off_val, off_mean, off_stat, total; };
+struct FlatWorkspace { long long off_val, off_mean, off_stat, total; };
 
 FlatWorkspace flat_workspace_layout(const PlaneSumPlan& pl) {
     FlatWorkspace w;
     long long o = 0;
     const long long nl = (long long)pl.leaf_off.size(), nn = (long long)pl.node_l.size();
-    w.off_leaf_off = o; o = align16(o + 4 * nl);
-    w.off_leaf_len = o; o = align16(o + 4 * nl);
-    w.off_node_l = o; o = align16(o + 4 * nn);
-    w.off_node_r = o; o = align16(o + 4 * nn);
-    w.off_group = o; o = align16(o + 4 * (long long)pl.group_start.size());
     w.off_val = o; o = align16(o + 4 * 4 * (nl + nn));
     w.off_mean = o; o = align16(o + 16);
     w.off_stat = o; o = align16(o + 32);
@@ -561,24 +558,39 @@ FlatWorkspace flat_workspace_layout(const PlaneSumPlan& pl) {
     return w;
 }
 
-// uploads the tree tables into the workspace and launches the two summation kernels; mean[4] lands at ws + off_mean
+// device copy of the tree tables (cached per device), then the two summation kernels; mean[4] lands at ws + off_mean
 int launch_plane_means(const float* mosaic, long long pitch, int H, int W, char* ws, const PlaneSumPlan& pl, const FlatWorkspace& lay,
                        PlaneSumTables* tables, cudaStream_t stream) {
     const int nl = (int)pl.leaf_off.size(), nn = (int)pl.node_l.size(), ng = (int)pl.group_start.size() - 1;
-    cudaError_t e = cudaMemcpyAsync(ws + lay.off_leaf_off, pl.leaf_off.data(), 4LL * nl, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + lay.off_leaf_len, pl.leaf_len.data(), 4LL * nl, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && nn) e = cudaMemcpyAsync(ws + lay.off_node_l, pl.node_l.data(), 4LL * nn, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess && nn) e = cudaMemcpyAsync(ws + lay.off_node_r, pl.node_r.data(), 4LL * nn, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + lay.off_group, pl.group_start.data(), 4LL * (ng + 1), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "plane means: table upload: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* d = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(pl.dev_mu);
+        auto it = pl.dev_tables.find(dev);
+        if (it != pl.dev_tables.end()) {
+            d = it->second;
+        } else {
+            const size_t ints = 2 * (size_t)nl + 2 * (size_t)nn + (size_t)ng + 1;
+            std::vector<int> host;
+            host.reserve(ints);
+            host.insert(host.end(), pl.leaf_off.begin(), pl.leaf_off.end());
+            host.insert(host.end(), pl.leaf_len.begin(), pl.leaf_len.end());
+            host.insert(host.end(), pl.node_l.begin(), pl.node_l.end());
+            host.insert(host.end(), pl.node_r.begin(), pl.node_r.end());
+            host.insert(host.end(), pl.group_start.begin(), pl.group_start.end());
+            cudaError_t e = cudaMalloc((void**)&d, ints * 4);
+            if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), ints * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "plane means: table upload: %s", cudaGetErrorString(e));
+            pl.dev_tables[dev] = d;
+        }
+    }
     PlaneSumTables t;
-    t.leaf_off = (const int*)(ws + lay.off_leaf_off); t.leaf_len = (const int*)(ws + lay.off_leaf_len);
-    t.node_l = (const int*)(ws + lay.off_node_l); t.node_r = (const int*)(ws + lay.off_node_r);
-    t.group_start = (const int*)(ws + lay.off_group);
+    t.leaf_off = d; t.leaf_len = d + nl; t.node_l = d + 2 * nl; t.node_r = d + 2 * nl + nn; t.group_start = d + 2 * nl + 2 * nn;
     t.n_leaves = nl; t.n_nodes = nn; t.n_groups = ng;
     t.val = (float*)(ws + lay.off_val);
     *tables = t;
-    leaf_sum_kernel<<<grid_for(4LL * nl, 128), 128, 0, stream>>>(mosaic, pitch, W, t);
+    leaf_sum_kernel<<<grid_for(32LL * nl, 256), 256, 0, stream>>>(mosaic, pitch, W, t);   // eight lanes per (plane, leaf)
     int rc = check_launch("leaf_sum_kernel");
     if (rc) return rc;
     const long long n = (long long)(H / 2) * (W / 2);

@@ -153,12 +153,22 @@ PYSP_HD float dot3_f64(const double* m, float c0, float c1, float c2) {
 #endif
 }
 
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float exp2f_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
 PYSP_HD float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
-// colorize/transform.py:98-99 in float32
-PYSP_NOINLINE float srgb_gamma(float v) {
+// colorize/transform.py:98-99 in float32.  x^(1/2.4) = exp2(log2(x) / 2.4) with the hardware approximations (MUFU.LG2 /
+// MUFU.EX2): relative error of the curve about 1e-6, inside the 1e-4 the parity contract states for the gamma.
+PYSP_HD float srgb_gamma(float v) {
     float x = clip01(v);
-    return x <= 0.0031308f ? x * 12.92f : (1.055f * powf(x, (float)(1.0 / 2.4))) - 0.055f;
+#ifdef __CUDA_ARCH__
+    const float pw = exp2f_fast(__log2f(x) * (float)(1.0 / 2.4));
+#else
+    const float pw = powf(x, (float)(1.0 / 2.4));
+#endif
+    return x <= 0.0031308f ? x * 12.92f : (1.055f * pw) - 0.055f;
 }
 
 // ---- cv2 RGB->Lab (float32 path) : quantise, trilinear in the 33^3 int16 table -----------------------

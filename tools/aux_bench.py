@@ -1,0 +1,74 @@
+"""Device-resident timing of the kernels either side of the develop path on a 24 MP frame (CUDA events, L2 flushed
+between repetitions) with their HBM roofline: algorithmic bytes / time against MEASURED_PEAKS.json (fallback 6552 GB/s).
+    python tools/aux_bench.py            # one JSON object
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from pysp_b200 import engine, synthetic as syn  # noqa: E402
+from pysp_b200.colour import cam_to_rgb_matrix  # noqa: E402
+from pysp_b200.wb_cct import CameraWhiteBalance  # noqa: E402
+
+H, W = 4000, 6000
+peak = 6552.3
+pk = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peak = float(json.load(open(pk)).get("hbm_gbs", peak))
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timed(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        flush.zero_()                                   # 256 MB write: evicts the 126 MB L2
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+rng = np.random.default_rng(0)
+sensor = engine.to_device(rng.random((H, W), dtype=np.float32))
+flat = engine.to_device((0.5 + 0.5 * rng.random((H, W), dtype=np.float32)).astype(np.float32))
+res = {}
+
+
+def report(name, ms, nbytes, note):
+    gbs = nbytes / ms / 1e6
+    res[name] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1), "peak_gbs": peak,
+                 "frac": round(gbs / peak, 3), "mpix_s": round(H * W / ms / 1e3, 1), "bytes": note}
+
+
+report("bayer_plane_means", timed(lambda: engine.bayer_plane_means(flat)), 4 * H * W, "4 B/px read")
+report("flat_frame_correction", timed(lambda: engine.flat_frame_correction(sensor, flat)), 12 * H * W,
+       "4 (image) + 4 (flat) read + 4 written per px; the implementation reads the flat 3x and the image 2x")
+report("find_hot_pixels_threshold", timed(lambda: engine.find_hot_pixels_threshold(sensor, 0.025, 5)), 5 * H * W, "4 read + 1 written per px")
+wbc = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+m = cam_to_rgb_matrix(wbc.get_matrix())
+wb = wbc.get_reciprocal_multipliers()
+n = 3
+imgs = [engine.to_device(rng.random((H, W, 3), dtype=np.float32)) for _ in range(n)]
+offs = [0.5, 1.0, 2.0]
+args = (wb, float(max(wb)), [False] * n, [np.float32(o) for o in offs], [np.float32(1.6 ** (-0.1 * o)) for o in offs], 2, 2.0, m)
+report("fuse_exposures_from_debayer_n3", timed(lambda: engine.fuse_exposures_from_debayer(imgs, *args)), (12 * n * 2 + 24) * H * W,
+       "n x 12 read + n x 12 written back + 12 (image) + 12 (count) per px, n = 3")
+rgb = imgs[0]
+report("cam_to_lin_srgb", timed(lambda: engine.cam_to_rgb(rgb, m)), 24 * H * W, "12 read + 12 written per px")
+report("lin_srgb_to_srgb", timed(lambda: engine.srgb_gamma(rgb)), 24 * H * W, "12 read + 12 written per px")
+raw = engine.to_device(syn.scene(H, W, 0))
+report("bayer_normalize", timed(lambda: engine.normalize(raw, syn.BLACK, syn.WHITE)), 6 * H * W, "2 read + 4 written per px")
+br = [engine.to_device(rng.random((H, W), dtype=np.float32)) for _ in range(5)]
+bias = np.ones((5, 3), np.float32)
+report("fuse_exposures_to_raw_n5", timed(lambda: engine.fuse_exposures(br, [0.25, 0.5, 1, 2, 4], bias, 4)), (4 * 5 + 8) * H * W,
+       "5 x 4 read + 4 (mosaic) + 4 (count) written per px")
+print(json.dumps({"frame": [H, W], "peak_source": "MEASURED_PEAKS.json" if os.path.exists(pk) else "fallback", "kernels": res}))
