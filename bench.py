@@ -264,15 +264,23 @@ def main():
         dom = max(per, key=lambda k: per[k])
         chain_ms = sum(per.values())
         ach = ALGO_BYTES_PER_PX[dom] * px_per_frame / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
-        traffic = None
+        traffic, issue = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = prof.get(dom)
+            # the path is issue-bound, not HBM-bound: warp instructions per launch (ncu) over the
+            # 148 SMs x 4 schedulers x 1 instruction/clock gives the floor the measured launch time is compared with
+            clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            issue = {k: {"warp_inst_per_launch": v, "thread_inst_per_px": 32.0 * v / px_per_frame,
+                         "issue_floor_ms": 1e3 * v / (148 * 4 * clk),
+                         "issue_frac": (1e3 * v / (148 * 4 * clk)) / per[k] if per.get(k) else None}
+                     for k, v in prof.get("inst", {}).items()}
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX[dom] * px_per_frame,
-                    "ms_per_launch": per, "launches": {names[k]: int(cnt[k]) for k in range(2)},
+                    "ms_per_launch": per, "launches": {names[k]: int(cnt[k]) for k in range(2)}, "issue": issue,
                     "chain": {"bytes_per_px": 14.0, "ms_per_frame": chain_ms,
                               "achieved": 14.0 * px_per_frame / (chain_ms * 1e-3) / 1e9 if chain_ms else 0.0,
                               "frac": (14.0 * px_per_frame / (chain_ms * 1e-3) / 1e9 / peak) if chain_ms else 0.0}}
