@@ -179,8 +179,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        parallel.quiet_nccl_stdout()                                 # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
+    all_cpus = os.sched_getaffinity(0)
+    numa = parallel.bind_to_gpu_numa_node(local_rank)   # pinned staging buffers of the e2e leg on the GPU's socket
 
     cam_wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
     wb = cam_wb.get_reciprocal_multipliers()
@@ -249,7 +252,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * len(host) * e2e_steps * px_per_frame / float(t.item()) / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": len(host) * pipe.h2d_bytes(), "d2h_bytes_per_step": len(host) * pipe.d2h_bytes(),
-               "steps": e2e_steps, "api": "pysp_b200.pipeline.FramePipeline.run (pinned host in/out, 3 streams)"}
+               "steps": e2e_steps, "api": "pysp_b200.pipeline.FramePipeline.run (pinned host in/out, 3 streams)", "numa_node": numa}
         # light check that the pipeline produced the device-resident result
         ref0 = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
         engine.develop(frames[0], out_tensor=ref0, **kw)
@@ -295,6 +298,7 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)           # the CPU arm gets every host thread back
             threads = os.cpu_count() or 1
             os.environ["OMP_NUM_THREADS"] = str(threads)
             once, kind = cpu_port(CPU_SAMPLE, threads)

@@ -11,8 +11,40 @@ The reference has no distributed code; the path shards naturally (SURVEY.md sect
                                      in list order, like raw_hdr.py:135-139, bit for bit.
 The exchange helpers work on CUDA tensors with the NCCL backend and on CPU tensors with gloo (tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def quiet_nccl_stdout():
+    """NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout; tools that print one JSON line keep stdout clean."""
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: run this process (and first-touch its pinned staging buffers) on the CPU socket the GPU's PCIe
+    root hangs off, so that host<->device copies do not cross the socket interconnect.  Best effort; returns the NUMA node
+    or None when the topology cannot be read."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def frames_for_rank(n_frames, rank, world):

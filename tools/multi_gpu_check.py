@@ -24,6 +24,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    parallel.quiet_nccl_stdout()
+    parallel.bind_to_gpu_numa_node(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
     wbc = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
     wb, m = wbc.get_reciprocal_multipliers(), cam_to_rgb_matrix(wbc.get_matrix())
@@ -61,14 +63,15 @@ def main():
             mine[k] = torch.from_numpy(np.clip(base * np.float32(2.0 ** (2 - k)), 0, 1).astype(np.float32)).to(dev)
     halo = parallel.halo_rows(stages)
     tev, offs, bias = fusion_constants(evs, wb)
-    torch.cuda.synchronize(); dist.barrier()
-    t0 = time.perf_counter()
-    rows, hb = parallel.exchange_brackets_by_rows(mine, nb, Hh, halo, like=torch.empty((0, Wh), dtype=torch.float32, device=dev))
-    fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
-    bb, be = parallel.band_rows(Hh, world, rank)
-    hdr_out = engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=Hh, in_row0=hb)
-    torch.cuda.synchronize(); dist.barrier()
-    t_hdr = time.perf_counter() - t0
+    for _ in range(2):                                  # first pass sets the NCCL peer connections up; the second is timed
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        rows, hb = parallel.exchange_brackets_by_rows(mine, nb, Hh, halo, like=torch.empty((0, Wh), dtype=torch.float32, device=dev))
+        fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
+        bb, be = parallel.band_rows(Hh, world, rank)
+        hdr_out = engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=Hh, in_row0=hb)
+        torch.cuda.synchronize(); dist.barrier()
+        t_hdr = time.perf_counter() - t0
     sums = [None] * world
     dist.all_gather_object(sums, (bb, be, hdr_out.view(torch.int32).to(torch.int64).sum().item()))
     ok_hdr = True
