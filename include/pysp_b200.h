@@ -106,6 +106,10 @@ int pysp_normalize_u16(const uint16_t* in, int64_t in_pitch_bytes, float* out, i
 int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n_pixels, const double m[9], int32_t clip,
                          int32_t apply_gamma, int32_t out_f16, void* stream);
 
+/* cv2.cvtColor(float32 RGB -> Lab) as the homogeneity metric uses it (debayer/ahd.py:58,62), stand-alone for stage tests:
+ * n_pixels RGB float32 -> Lab float32.  `lab_lut` is the packed device table (pysp_lab_lut_pack_host). */
+int pysp_rgb_to_lab_cv2(const float* in, float* out, int64_t n_pixels, const void* lab_lut, void* stream);
+
 /* lin_srgb_to_srgb (colorize/transform.py:89-99) on n float32 values. */
 int pysp_lin_srgb_to_srgb(const float* in, float* out, int64_t n_values, void* stream);
 

@@ -92,6 +92,18 @@ __global__ void __launch_bounds__(256) matrix_kernel(MatrixParams p) {
     }
 }
 
+// cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) alone (debayer/ahd.py:58,62), for stage tests: the same lab_lookup the fused
+// kernel calls, unpacked to float Lab exactly as cv2 returns it (L = v*100/16384, a/b = v/64 - 128)
+struct LabParams { const float* in; float* out; long long n; const uint4* lut; };
+__global__ void __launch_bounds__(256) lab_kernel(LabParams p) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+        const LabQ q = lab_lookup(p.lut, p.in[3 * i], p.in[3 * i + 1], p.in[3 * i + 2]);
+        p.out[3 * i] = q.L;
+        p.out[3 * i + 1] = ((float)(q.ab & 0xFFFFu) * 0.015625f) - 128.0f;
+        p.out[3 * i + 2] = ((float)(q.ab >> 16) * 0.015625f) - 128.0f;
+    }
+}
+
 __global__ void __launch_bounds__(256) gamma_kernel(GammaParams p) {
     const long long n4 = (((size_t)p.in | (size_t)p.out) % 16 == 0) ? p.n / 4 : 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

@@ -459,6 +459,16 @@ int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n, const double m[9
     return check_launch("matrix_kernel");
 }
 
+int pysp_rgb_to_lab_cv2(const float* in, float* out, int64_t n, const void* lab_lut, void* stream) {
+    if (!in || !out || !lab_lut || n < 0) return fail(PYSP_ERR_INVALID, "pysp_rgb_to_lab_cv2: bad argument");
+    if (n == 0) return PYSP_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    LabParams p = {in, out, n, (const uint4*)lab_lut};
+    lab_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("lab_kernel");
+}
+
 int pysp_lin_srgb_to_srgb(const float* in, float* out, int64_t n, void* stream) {
     if (!in || !out || n < 0) return fail(PYSP_ERR_INVALID, "pysp_lin_srgb_to_srgb: bad argument");
     if (n == 0) return PYSP_OK;

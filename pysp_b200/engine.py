@@ -168,6 +168,18 @@ def cam_to_rgb(rgb, matrix, clip=True, gamma=False, half=False, stream=None):
     return out
 
 
+def rgb_to_lab_cv2(rgb, stream=None):
+    """cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) on the device (the homogeneity metric's Lab; for stage tests)."""
+    require_cuda()
+    L = _capi.lib()
+    rgb = rgb.contiguous()
+    out = torch.empty_like(rgb)
+    with torch.cuda.device(rgb.device):
+        _capi.check(L.pysp_rgb_to_lab_cv2(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, lab_lut(rgb.device).data_ptr(),
+                                          _stream_ptr(stream)))
+    return out
+
+
 def srgb_gamma(rgb, stream=None):
     require_cuda()
     L = _capi.lib()

@@ -248,3 +248,23 @@ def test_large_frame_smoke(eng):
     del a
     b = eng.develop(raw, WB, M, stages=1, black=syn.BLACK, white=syn.WHITE)
     assert b.view(torch.int32).to(torch.int64).sum().item() == s1
+
+
+def test_lab_exhaustive_against_cv2(eng):
+    """cv2's float32 RGB->Lab quantises each channel to cvRound(v*16384) and only uses bits 5..14 of it: 513 distinct
+    levels per channel.  Every one of the 513^3 keys goes through the kernel's lab_lookup and through cv2.cvtColor:
+    bit-identical Lab (parity gate iii)."""
+    cv2 = pytest.importorskip("cv2")
+    lv = (np.arange(513, dtype=np.float32) * np.float32(32.0 / 16384.0)).astype(np.float32)
+    g, b = np.meshgrid(lv, lv, indexing="ij")
+    bad = 0
+    for r in lv:
+        x = np.stack([np.full_like(g, r), g, b], axis=-1)                 # [513, 513, 3]
+        want = cv2.cvtColor(x, cv2.COLOR_RGB2LAB)
+        got = eng.rgb_to_lab_cv2(torch.from_numpy(x).cuda()).cpu().numpy()
+        bad += int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    assert bad == 0, "%d of %d Lab values differ from cv2" % (bad, 3 * 513 ** 3)
+    # off-grid and out-of-range inputs
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-0.3, 1.4, size=(1, 2_000_000, 3)).astype(np.float32)
+    assert_bit_equal(eng.rgb_to_lab_cv2(torch.from_numpy(x).cuda()).cpu().numpy(), cv2.cvtColor(x, cv2.COLOR_RGB2LAB), "Lab")
