@@ -56,7 +56,7 @@ def main():
     # ---- flat_frame_correction
     cases = [("aux_flat34x50", 34, 50, dict(), False), ("aux_flat130x70_zeros", 130, 70, dict(zeros=9, negatives=5), False),
              ("aux_flat64x96_clamp_dead", 64, 96, dict(zeros=3, dead_plane=True), True),
-             ("aux_flat400x600", 400, 600, dict(zeros=2), False)]
+             ("aux_flat200x304", 200, 304, dict(zeros=2), False)]
     for name, h, w, kw, clamp in cases:
         sensor = sensor_of(syn.scene(h, w, 31))
         sensor[sensor < 0.05] = f32(0.05)      # keep 0/0 out (a NaN plane maximum is not defined by the reference)

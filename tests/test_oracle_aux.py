@@ -8,7 +8,7 @@ from oracle import ahd_spec as sp
 from oracle import aux_spec as ax
 from pysp_b200 import synthetic as syn
 
-FLAT = ["aux_flat34x50", "aux_flat130x70_zeros", "aux_flat64x96_clamp_dead", "aux_flat400x600"]
+FLAT = ["aux_flat34x50", "aux_flat130x70_zeros", "aux_flat64x96_clamp_dead", "aux_flat200x304"]
 HOT = ["aux_hot34x50", "aux_hot66x130", "aux_hot8x8"]
 FUSE = ["aux_fusecam24x40", "aux_fusecam16x12_norm", "aux_fusecam20x28_nondyadic"]
 
