@@ -1,0 +1,14 @@
+import sys, os
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+from pysp_b200 import engine
+rng = np.random.default_rng(0)
+H, W = 4000, 6000
+sensor = engine.to_device(rng.random((H, W), dtype=np.float32))
+flat = engine.to_device((0.5 + 0.5 * rng.random((H, W), dtype=np.float32)).astype(np.float32))
+for _ in range(2):
+    engine.flat_frame_correction(sensor, flat)
+    engine.find_hot_pixels_threshold(sensor, 0.025, 5)
+    br = [sensor, flat, sensor, flat, sensor]
+    engine.fuse_exposures(br, [0.25, 0.5, 1, 2, 4], np.ones((5, 3), np.float32), 4)
+torch.cuda.synchronize()

@@ -36,13 +36,26 @@ def main():
     # --- row bands: every rank starts with ONLY its band of the mosaic on its GPU ---
     b, e = parallel.band_rows(H, world, rank)
     band = torch.from_numpy(frame[b:e].view(np.int16)).to(dev)
-    for _ in range(2):                                  # first pass warms NCCL up; the second is timed
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        out = parallel.develop_band(band, H, stages, lambda held, hb, rows: engine.develop(
-            held, rows=rows, frame_height=H, in_row0=hb, **kw))
-        torch.cuda.synchronize(); dist.barrier()
-        t_band = time.perf_counter() - t0
+    def device_ms(fn, reps=3):
+        """max over ranks of the device time of fn (CUDA events on the current stream), best of `reps` after a warm-up"""
+        fn()
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize(); dist.barrier()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b_.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        return r, best
+
+    out, t_band = device_ms(lambda: parallel.develop_band(band, H, stages, lambda held, hb, rows: engine.develop(
+        held, rows=rows, frame_height=H, in_row0=hb, **kw)))
+    _, t_exch = device_ms(lambda: parallel.exchange_halo(band, H, stages))
+    t_band, t_exch = t_band * 1e-3, t_exch * 1e-3
     # reference: rank 0 develops the whole frame alone and compares every band
     checks = [None] * world
     dist.all_gather_object(checks, (b, e, out.view(torch.int32).to(torch.int64).sum().item()))
@@ -63,15 +76,15 @@ def main():
             mine[k] = torch.from_numpy(np.clip(base * np.float32(2.0 ** (2 - k)), 0, 1).astype(np.float32)).to(dev)
     halo = parallel.halo_rows(stages)
     tev, offs, bias = fusion_constants(evs, wb)
-    for _ in range(2):                                  # first pass sets the NCCL peer connections up; the second is timed
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
+    bb, be = parallel.band_rows(Hh, world, rank)
+
+    def hdr_step():
         rows, hb = parallel.exchange_brackets_by_rows(mine, nb, Hh, halo, like=torch.empty((0, Wh), dtype=torch.float32, device=dev))
         fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
-        bb, be = parallel.band_rows(Hh, world, rank)
-        hdr_out = engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=Hh, in_row0=hb)
-        torch.cuda.synchronize(); dist.barrier()
-        t_hdr = time.perf_counter() - t0
+        return engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=Hh, in_row0=hb)
+
+    hdr_out, t_hdr = device_ms(hdr_step)
+    t_hdr *= 1e-3
     sums = [None] * world
     dist.all_gather_object(sums, (bb, be, hdr_out.view(torch.int32).to(torch.int64).sum().item()))
     ok_hdr = True
@@ -82,7 +95,8 @@ def main():
         for (x0, x1, s) in sums:
             ok_hdr &= (whole[x0:x1].view(torch.int32).to(torch.int64).sum().item() == s)
         print(json.dumps({"n_gpus": world, "bands_100MP_bit_identical": bool(ok_bands), "bands_100MP_s": t_band,
-                          "bands_100MP_Mpix_s": H * W / t_band / 1e6, "hdr5_24MP_bit_identical": bool(ok_hdr),
+                          "bands_100MP_Mpix_s": H * W / t_band / 1e6, "halo_exchange_s": t_exch,
+                          "timing": "CUDA events, max over ranks, best of 3", "hdr5_24MP_bit_identical": bool(ok_hdr),
                           "hdr5_24MP_s": t_hdr}))
     dist.barrier()
     dist.destroy_process_group()
