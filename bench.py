@@ -174,6 +174,9 @@ def main():
     from pysp_b200.wb_cct import CameraWhiteBalance
     import ctypes as C
 
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -307,7 +310,8 @@ def main():
             line["cpu_baseline"] = {"value": CPU_SAMPLE[0] * CPU_SAMPLE[1] / best / 1e6, "unit": "Mpix/s", "cores": threads,
                                     "kind": kind, "sample": "%dx%d crop of frame 0, best of 2 after 1 warm-up" % (
                                         CPU_SAMPLE[1], CPU_SAMPLE[0])}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

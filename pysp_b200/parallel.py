@@ -108,6 +108,102 @@ def exchange_halo(band, height, stages, group=None):
     return held, hb
 
 
+class SymmetricBand:
+    """Row band of one large frame in NVLink-shared ("symmetric") memory: every rank allocates the same buffer, maps its
+    peers' buffers (torch.distributed._symmetric_memory: CUDA IPC over NVLink / NVSwitch) and *pulls* the raw halo rows
+    it needs straight out of its neighbours' HBM with peer-to-peer copies -- no NCCL kernel, no staging copy of the band.
+
+        sb = SymmetricBand(height, width, torch.int16, stages)      # collective: all ranks of the group
+        sb.band().copy_(my_rows)                                     # or decode / upload straight into sb.band()
+        held, held_begin = sb.exchange()                             # stream-ordered; held = band +- halo rows
+        out = engine.develop(held, ..., rows=sb.rows, frame_height=height, in_row0=held_begin)
+
+    Results are bit-identical to the NCCL path (`exchange_halo`) and to one GPU.  CUDA only; the CPU tests cover the
+    same row arithmetic through `exchange_halo` on gloo."""
+
+    def __init__(self, height, width, dtype, stages, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.height, self.width, self.stages, self.dtype = int(height), int(width), int(stages), dtype
+        self.ranges = [band_with_halo(self.height, self.world, r, self.stages) for r in range(self.world)]
+        b, e, hb, he = self.ranges[self.rank]
+        self.rows, self.held_begin, self.held_rows = (b, e), hb, he - hb
+        self.max_rows = max(r[3] - r[2] for r in self.ranges)
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty((self.max_rows, self.width), dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.peers = {}
+        for peer in range(self.world):
+            if peer != self.rank:
+                pb, pe, phb, phe = self.ranges[peer]
+                r0, r1 = max(pb, hb), min(pe, he)          # rows of the peer's band that I hold as halo
+                if r0 < r1:
+                    view = self.handle.get_buffer(peer, (self.max_rows, self.width), dtype, 0)
+                    self.peers[peer] = (view[r0 - phb:r1 - phb], self.buf[r0 - hb:r1 - hb])
+
+    def band(self):
+        """[band_rows, W] view of the shared buffer where this rank's own rows live."""
+        b, e = self.rows
+        return self.buf[b - self.held_begin:e - self.held_begin]
+
+    def exchange(self):
+        """Pull the neighbours' halo rows (peer-to-peer copies on the current stream, fenced by device-side barriers)."""
+        self.handle.barrier(channel=0)                      # every rank's band is in place
+        for src, dst in self.peers.values():
+            dst.copy_(src, non_blocking=True)
+        self.handle.barrier(channel=1)                      # nobody overwrites a band that is still being read
+        return self.buf[:self.held_rows], self.held_begin
+
+
+class SymmetricBrackets:
+    """HDR brackets of one scene spread over the ranks (bracket k lives on rank k % world) in NVLink-shared memory.
+    `views(rank_rows)` returns, for every bracket in list order, a tensor over the OWNER's HBM restricted to this rank's
+    rows: handing those to `engine.fuse_exposures` makes the fuse kernel read its operands over NVLink / NVSwitch while
+    it accumulates them in list order -- exchange and compute are one kernel, nothing is staged, and the float32 sums
+    are those of raw_hdr.py:135-139 bit for bit.
+
+        sbr = SymmetricBrackets(height, width, n_brackets, halo_rows(stages))   # collective
+        sbr.slot(k).copy_(bracket_k)          # on the owner of bracket k
+        rows, held_begin = sbr.views()        # after sbr.ready()
+    """
+
+    def __init__(self, height, width, n_brackets, halo, group=None, device=None, dtype=torch.float32):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.height, self.width, self.n = int(height), int(width), int(n_brackets)
+        self.slots = (self.n + self.world - 1) // self.world
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty((self.slots, self.height, self.width), dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.buf, group)
+        b, e = band_rows(self.height, self.world, self.rank)
+        self.rows = (b, e)
+        self.held = (max(0, b - halo), min(self.height, e + halo))
+        self._peer = {r: (self.buf if r == self.rank else
+                          self.handle.get_buffer(r, (self.slots, self.height, self.width), dtype, 0)) for r in range(self.world)}
+
+    def owner(self, k):
+        return k % self.world
+
+    def slot(self, k):
+        """[H, W] view of bracket k on its owner (call on rank owner(k))."""
+        assert self.owner(k) == self.rank
+        return self.buf[k // self.world]
+
+    def ready(self):
+        """Device-side barrier on the current stream: every owner's brackets are in place."""
+        self.handle.barrier(channel=0)
+
+    def done(self):
+        """Device-side barrier: every rank has finished reading (call before brackets are overwritten)."""
+        self.handle.barrier(channel=1)
+
+    def views(self):
+        hb, he = self.held
+        return [self._peer[self.owner(k)][k // self.world, hb:he] for k in range(self.n)], hb
+
+
 def exchange_brackets_by_rows(my_brackets, n_brackets, height, halo, group=None, like=None):
     """HDR brackets live on rank (index % world) as whole [H, W] float32 mosaics (`my_brackets` maps
     bracket index -> tensor).  Returns the list of all n brackets restricted to this rank's rows
