@@ -106,6 +106,15 @@ int pysp_normalize_u16(const uint16_t* in, int64_t in_pitch_bytes, float* out, i
 int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n_pixels, const double m[9], int32_t clip,
                          int32_t apply_gamma, int32_t out_f16, void* stream);
 
+/* RawDemosaicData.wb_apply / wb_undo (base_types/image_base.py:45-60) and clip_rgb (colorize/transform.py:6-19) on
+ * n_pixels RGB float32.  mode 0 (PYSP_WB_APPLY): x * wb[c] in float32.  mode 1 (PYSP_WB_UNDO): float32(float64(x) / wb[c]),
+ * after x * max_wb in float32 when `normalized`.  mode 2 (PYSP_CLIP01): clip to [0,1].  `out` may alias `in`. */
+#define PYSP_WB_APPLY 0
+#define PYSP_WB_UNDO 1
+#define PYSP_CLIP01 2
+int pysp_wb_scale(const float* in, float* out, int64_t n_pixels, const float wb[3], float max_wb, int32_t mode,
+                  int32_t normalized, void* stream);
+
 /* cv2.cvtColor(float32 RGB -> Lab) as the homogeneity metric uses it (debayer/ahd.py:58,62), stand-alone for stage tests:
  * n_pixels RGB float32 -> Lab float32.  `lab_lut` is the packed device table (pysp_lab_lut_pack_host). */
 int pysp_rgb_to_lab_cv2(const float* in, float* out, int64_t n_pixels, const void* lab_lut, void* stream);

@@ -9,6 +9,7 @@ from enum import IntEnum, auto
 import numpy as np
 import torch
 
+from .. import engine
 from .._arrays import as_cuda, give_back, is_numpy
 from ..colorize.transform import cam_to_lin_srgb
 from ..const import QualityDemosaic  # noqa: F401
@@ -37,25 +38,22 @@ class RawDemosaicData:
         return (self.image is not None and self._wb_coeff is not None
                 and type(self.mat_xyz) != type(MatXyzToCamera) and self.current_ev != np.inf)
 
-    def _wb3(self, dtype):
-        return torch.as_tensor(np.asarray(self._wb_coeff[:3]), dtype=dtype, device=as_cuda(self.image).device)
-
     def wb_apply(self):
-        """Multiply the white-balance coefficients in, if they are not applied already."""
+        """Multiply the white-balance coefficients in, if they are not applied already (float32, image_base.py:45-49)."""
         if not self._wb_applied:
             want_np = is_numpy(self.image)
             img = as_cuda(self.image, torch.float32)
-            self.image = give_back((img * self._wb3(torch.float32)).to(torch.float32), want_np)
+            self.image = give_back(engine.wb_scale(img, np.asarray(self._wb_coeff, dtype=np.float32), engine.WB_APPLY), want_np)
             self._wb_applied = True
 
     def wb_undo(self):
-        """Return to pure camera space (float64 division, as the reference does)."""
+        """Return to pure camera space: float64 division, after removing the normalisation (image_base.py:52-60)."""
         if self._wb_applied:
             want_np = is_numpy(self.image)
             img = as_cuda(self.image, torch.float32)
-            if self._wb_normalized:
-                img = img * float(max(self._wb_coeff))
-            self.image = give_back((img.to(torch.float64) / self._wb3(torch.float64)).to(torch.float32), want_np)
+            wb = np.asarray(self._wb_coeff, dtype=np.float32)
+            self.image = give_back(engine.wb_scale(img, wb, engine.WB_UNDO, normalized=self._wb_normalized,
+                                                   max_wb=float(max(wb))), want_np)
             self._wb_applied = False
             self._wb_normalized = False
 

@@ -13,7 +13,7 @@ from ..colour import LinRgbColorspace, cam_to_rgb_matrix
 def clip_rgb(rgb):
     """Clip an RGB image to [0,1] (transform.py:6-19)."""
     want_np = is_numpy(rgb)
-    return give_back(torch.clamp(as_cuda(rgb, torch.float32), 0.0, 1.0), want_np)
+    return give_back(engine.wb_scale(as_cuda(rgb, torch.float32), None, engine.CLIP01), want_np)
 
 
 def cam_to_rgb_norm(rgb, cam_xyz_matrix, destination_colorspace, clip_highlights=True):

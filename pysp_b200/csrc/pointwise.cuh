@@ -92,6 +92,26 @@ __global__ void __launch_bounds__(256) matrix_kernel(MatrixParams p) {
     }
 }
 
+// RawDemosaicData.wb_apply / wb_undo (base_types/image_base.py:45-60) and clip_rgb (colorize/transform.py:6-19) on
+// [n][3] float32 pixels.  mode 0: x * wb[c] (float32).  mode 1: float32(float64(x [* max_wb]) / wb[c]).  mode 2: clip to [0,1].
+struct WbParams { const float* in; float* out; long long n; float wb[3]; float max_wb; int mode; int normalized; };
+__global__ void __launch_bounds__(256) wb_kernel(WbParams p) {
+    const long long total = 3 * p.n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 3);
+        float v = p.in[i];
+        if (p.mode == 0) {
+            v = v * p.wb[c];
+        } else if (p.mode == 1) {
+            if (p.normalized) v = v * p.max_wb;
+            v = __double2float_rn(__ddiv_rn((double)v, (double)p.wb[c]));
+        } else {
+            v = fminf(fmaxf(v, 0.0f), 1.0f);
+        }
+        p.out[i] = v;
+    }
+}
+
 // cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) alone (debayer/ahd.py:58,62), for stage tests: the same lab_lookup the fused
 // kernel calls, unpacked to float Lab exactly as cv2 returns it (L = v*100/16384, a/b = v/64 - 128)
 struct LabParams { const float* in; float* out; long long n; const uint4* lut; };

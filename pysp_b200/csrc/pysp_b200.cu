@@ -360,6 +360,34 @@ static int resident_ctas(const void* kernel, int threads, int smem_bytes, int* o
     return PYSP_OK;
 }
 
+// Per-device launch set-up of the develop chain (shared-memory opt-in, persistent grid sizes), done once per device
+struct ChainSetup { int grid_ahd, grid_eag, grid_median; };
+
+static int chain_setup(const ChainSetup** out) {
+    static std::mutex mu;
+    static std::map<int, ChainSetup> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(PYSP_ERR_CUDA, "no current CUDA device");
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it == cache.end()) {
+        const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
+        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_AHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        cudaError_t e2 = cudaFuncSetAttribute(median_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+        cudaError_t e3 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_EAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+            return fail(PYSP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+        ChainSetup cs;
+        int rc = resident_ctas((const void*)ahd_select_kernel<ALGO_AHD>, K1_THREADS, smem1, &cs.grid_ahd);
+        if (!rc) rc = resident_ctas((const void*)ahd_select_kernel<ALGO_EAG>, K1_THREADS, smem1, &cs.grid_eag);
+        if (!rc) rc = resident_ctas((const void*)median_stage_kernel, K2_THREADS, smem2, &cs.grid_median);
+        if (rc) return rc;
+        it = cache.emplace(dev, cs).first;
+    }
+    *out = &it->second;
+    return PYSP_OK;
+}
+
 int pysp_develop(const pysp_develop_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DevelopPlan plan;
@@ -375,17 +403,11 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
         if (bits & 4) plan.select.fast_div = 0;
     }
     const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;
-    {
-        cudaError_t e1 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_AHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-        cudaError_t e2 = cudaFuncSetAttribute(median_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-        cudaError_t e3 = cudaFuncSetAttribute(ahd_select_kernel<ALGO_EAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
-            return fail(PYSP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
-    }
-    const bool eag = plan.select.algo == ALGO_EAG;
-    int grid1 = 0, grid2 = 0;
-    rc = resident_ctas(eag ? (const void*)ahd_select_kernel<ALGO_EAG> : (const void*)ahd_select_kernel<ALGO_AHD>, K1_THREADS, smem1, &grid1);
+    const ChainSetup* cs = nullptr;
+    rc = chain_setup(&cs);
     if (rc) return rc;
+    const bool eag = plan.select.algo == ALGO_EAG;
+    const int grid1 = eag ? cs->grid_eag : cs->grid_ahd, grid2 = cs->grid_median;
     {
         CUtensorMap in_map;
         memset(&in_map, 0, sizeof(in_map));
@@ -403,10 +425,6 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
             else ahd_select_kernel<ALGO_AHD><<<grid, K1_THREADS, smem1, stream>>>(plan.select, in_map, om);
         }
         rc = check_launch("ahd_select_kernel");
-        if (rc) return rc;
-    }
-    if (plan.n_stages > 0) {
-        rc = resident_ctas((const void*)median_stage_kernel, K2_THREADS, smem2, &grid2);
         if (rc) return rc;
     }
     for (int s = 0; s < plan.n_stages; ++s) {
@@ -457,6 +475,19 @@ int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n, const double m[9
     for (int i = 0; i < 9; ++i) p.m[i] = m[i];
     matrix_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("matrix_kernel");
+}
+
+int pysp_wb_scale(const float* in, float* out, int64_t n, const float wb[3], float max_wb, int32_t mode, int32_t normalized,
+                  void* stream) {
+    if (!in || !out || n < 0 || mode < 0 || mode > 2 || (mode != 2 && !wb)) return fail(PYSP_ERR_INVALID, "pysp_wb_scale: bad argument");
+    if (n == 0) return PYSP_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    WbParams p;
+    p.in = in; p.out = out; p.n = n; p.max_wb = max_wb; p.mode = mode; p.normalized = normalized;
+    for (int c = 0; c < 3; ++c) p.wb[c] = wb ? wb[c] : 1.0f;
+    wb_kernel<<<grid_for(3 * n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("wb_kernel");
 }
 
 int pysp_rgb_to_lab_cv2(const float* in, float* out, int64_t n, const void* lab_lut, void* stream) {

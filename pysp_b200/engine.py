@@ -168,6 +168,24 @@ def cam_to_rgb(rgb, matrix, clip=True, gamma=False, half=False, stream=None):
     return out
 
 
+WB_APPLY, WB_UNDO, CLIP01 = 0, 1, 2
+
+
+def wb_scale(rgb, wb, mode, normalized=False, max_wb=1.0, stream=None):
+    """wb_apply / wb_undo / clip_rgb on a float32 [...,3] CUDA tensor (base_types/image_base.py:45-60, transform.py:6-19)."""
+    require_cuda()
+    L = _capi.lib()
+    rgb = rgb.contiguous()
+    if rgb.dtype != torch.float32 or rgb.shape[-1] != 3:
+        raise ValueError("wb_scale: float32 [...,3] tensor expected")
+    out = torch.empty_like(rgb)
+    wb3 = (C.c_float * 3)(*[float(v) for v in (wb[:3] if wb is not None else (1.0, 1.0, 1.0))])
+    with torch.cuda.device(rgb.device):
+        _capi.check(L.pysp_wb_scale(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, wb3, float(max_wb), int(mode),
+                                    int(bool(normalized)), _stream_ptr(stream)))
+    return out
+
+
 def rgb_to_lab_cv2(rgb, stream=None):
     """cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) on the device (the homogeneity metric's Lab; for stage tests)."""
     require_cuda()

@@ -158,9 +158,16 @@ def test_drop_in_containers(eng):
     rggb = img2.to_rggb()
     dem2 = rggb.demosaic(P.QualityDemosaic.Best, postprocess_steps=1)
     assert_bit_equal(dem2.image, d["cam"], "RawRggbBayerData.demosaic")
-    dem2.wb_undo()
-    dem2.wb_apply()
-    assert np.allclose(dem2.image, d["cam"], rtol=1e-6, atol=1e-7)
+    wbc = np.asarray(dem2._wb_coeff, dtype=np.float32)
+    dem2.wb_undo()                                     # base_types/image_base.py:52-60: float64 division, rounded to float32
+    undone = (d["cam"].astype(np.float64) / wbc[:3]).astype(np.float32)
+    assert_bit_equal(dem2.image, undone, "wb_undo")
+    dem2.wb_apply()                                    # image_base.py:45-49: float32 product
+    assert_bit_equal(dem2.image, (undone * wbc[:3]).astype(np.float32), "wb_apply")
+    norm = P.RawDemosaicData((d["cam"] / max(wbc)).astype(np.float32), wbc, wb_norm=True)
+    norm.wb_undo()
+    assert_bit_equal(norm.image, (((d["cam"] / max(wbc)).astype(np.float32) * max(wbc)).astype(np.float64) / wbc[:3]).astype(np.float32),
+                     "wb_undo of a normalised image")
     # CUDA tensors in -> CUDA tensors out
     img3 = P.RawRgbgDataFromRaw.from_mosaic(torch.from_numpy(d["raw"].view(np.int16)).cuda(), list(d["black"]),
                                             list(d["white"]), "Grbg", wb, ev=10.0)
