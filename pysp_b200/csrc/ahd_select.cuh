@@ -94,6 +94,22 @@ PYSP_HD void stage_pixel(float* out, const StoreParams& st, const FrameGeom& g, 
     }
 }
 
+// two horizontally adjacent finished pixels (tx even).  Planes leave as 8-byte pair stores (consecutive lanes write
+// consecutive pairs: no bank conflicts); the interleaved final layout keeps the per-pixel path (measured: pairs are not faster)
+template <int TW, int TH>
+PYSP_HD void stage_pixel_pair(float* out, const StoreParams& st, const FrameGeom& g, const ColorParams& c, int ty, int tx, Rgb v0, Rgb v1) {
+    if (st.mode == OUT_FINAL) {
+        stage_pixel<TW, TH>(out, st, g, c, ty, tx, v0);
+        stage_pixel<TW, TH>(out, st, g, c, ty, tx + 1, v1);
+    } else {
+        const int o = ty * TW + tx;
+        constexpr int PS = OutPlane<TW, TH>::FLOATS;
+        F2 a, b, d;
+        a.x = v0.r - v0.g; a.y = v1.r - v1.g; b.x = v0.b - v0.g; b.y = v1.b - v1.g; d.x = v0.g; d.y = v1.g;
+        *(F2*)(out + o) = a; *(F2*)(out + PS + o) = b; *(F2*)(out + 2 * PS + o) = d;
+    }
+}
+
 // generic (non-TMA) store of the staging tile, clipped to the destination views; converts to half if asked
 template <int TW, int TH>
 PYSP_HD void store_tile_generic(const float* out, const StoreParams& st, const FrameGeom& g, int x0, int y0) {
@@ -383,19 +399,27 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 // Lab of the metric image, kept for the tile + 2 px
                 float* oL = labL + dir * (L::LH * L::LW);
                 uint32_t* oAB = labAB + dir * (L::LH * L::LW);
+                LabQ q[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    LabQ q = metric_lab(p.c, p.lut, Rc[k], Gc[k], Bc[k]);
-                    int o = (2 * py + (k >> 1)) * L::LW + 2 * px + (k & 1);
-                    oL[o] = q.L; oAB[o] = q.ab;
+                for (int k = 0; k < 4; ++k) q[k] = metric_lab(p.c, p.lut, Rc[k], Gc[k], Bc[k]);
+                // the two pixels of a row leave as one 8-byte store (a 32-bit store per pixel has lane stride 2: two-way
+                // bank conflicts on every store)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int o = (2 * py + a) * L::LW + 2 * px;
+                    F2 l2; l2.x = q[2 * a].L; l2.y = q[2 * a + 1].L;
+                    U2 ab2; ab2.x = q[2 * a].ab; ab2.y = q[2 * a + 1].ab;
+                    *(F2*)(oL + o) = l2; *(U2*)(oAB + o) = ab2;
                 }
                 if (inner) {
                     float* oR = cand + (dir * 2 + 0) * (TH * TW);
                     float* oB = cand + (dir * 2 + 1) * (TH * TW);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        int o = (2 * (py - 1) + (k >> 1)) * TW + 2 * (px - 1) + (k & 1);
-                        oR[o] = Rc[k]; oB[o] = Bc[k];
+                    for (int a = 0; a < 2; ++a) {
+                        const int o = (2 * (py - 1) + a) * TW + 2 * (px - 1);
+                        F2 r2; r2.x = Rc[2 * a]; r2.y = Rc[2 * a + 1];
+                        F2 b2; b2.x = Bc[2 * a]; b2.y = Bc[2 * a + 1];
+                        *(F2*)(oR + o) = r2; *(F2*)(oB + o) = b2;
                     }
                 }
             }
@@ -542,20 +566,21 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 const uint32_t v0 = w0[a] + w0[a + 1] + w0[a + 2], v1 = w1[a] + w1[a + 1] + w1[a + 2];   // column sums
                 const uint32_t s = v0 + v1;                                    // (c0 + c2, c1 + c3)
                 const uint32_t t[2] = {(s & 0xFFFFu) + (v0 >> 16), (s >> 16) + (v1 & 0xFFFFu)};
+                const F2* ch = (const F2*)(cand + (ty + a) * TW + tx);         // tx even: one 8-byte load per plane
+                const F2 rh = ch[0], bh = ch[TH * TW / 2], rv = ch[TH * TW], bv = ch[3 * TH * TW / 2];
+                Rgb v[2];
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const int k = a * 2 + b;
                     const bool pick_h = (t[b] & 0xFFu) < (t[b] >> 8);          // sum_h < sum_v; ties -> V (ahd.py:139)
-                    int o = (ty + a) * TW + tx + b;
-                    Rgb v;
-                    v.r = pick_h ? cand[0 * TH * TW + o] : cand[2 * TH * TW + o];
-                    v.b = pick_h ? cand[1 * TH * TW + o] : cand[3 * TH * TW + o];
-                    if (k == 0) v.g = pick_h ? Q[L::P_GHR * QN + qi] : Q[L::P_GVR * QN + qi];
-                    else if (k == 1) v.g = Q[L::P_G1 * QN + qi];
-                    else if (k == 2) v.g = Q[L::P_G2 * QN + qi];
-                    else v.g = pick_h ? Q[L::P_GHB * QN + qi] : Q[L::P_GVB * QN + qi];
-                    stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty + a, tx + b, v);
+                    v[b].r = pick_h ? (b ? rh.y : rh.x) : (b ? rv.y : rv.x);
+                    v[b].b = pick_h ? (b ? bh.y : bh.x) : (b ? bv.y : bv.x);
+                    if (k == 0) v[b].g = pick_h ? Q[L::P_GHR * QN + qi] : Q[L::P_GVR * QN + qi];
+                    else if (k == 1) v[b].g = Q[L::P_G1 * QN + qi];
+                    else if (k == 2) v[b].g = Q[L::P_G2 * QN + qi];
+                    else v[b].g = pick_h ? Q[L::P_GHB * QN + qi] : Q[L::P_GVB * QN + qi];
                 }
+                stage_pixel_pair<TW, TH>(out, p.st, p.g, p.c, ty + a, tx, v[0], v[1]);
             }
         }
     }
