@@ -105,25 +105,29 @@ PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int t
         // the input planes hold the REPLICATE extension, so the windows of in-frame pixels are final
         float w[6][6], mr[4], mb[4];
         const int c = ly * L::AW + lx;                      // input-plane index of window cell (0,0) = pixel (y-2, x-2)
+        // lx and AW are even: a window row is three aligned 8-byte pairs (32-bit loads would have lane stride 2: two-way
+        // bank conflicts on every load)
 #pragma unroll
         for (int u = 0; u < 6; ++u)
 #pragma unroll
-            for (int v = 0; v < 6; ++v) w[u][v] = DR[c + u * L::AW + v];
+            for (int v = 0; v < 3; ++v) { const F2 t = ((const F2*)(DR + c + u * L::AW))[v]; w[u][2 * v] = t.x; w[u][2 * v + 1] = t.y; }
         median25_block2x2(w, mr);
 #pragma unroll
         for (int u = 0; u < 6; ++u)
 #pragma unroll
-            for (int v = 0; v < 6; ++v) w[u][v] = DB[c + u * L::AW + v];
+            for (int v = 0; v < 3; ++v) { const F2 t = ((const F2*)(DB + c + u * L::AW))[v]; w[u][2 * v] = t.x; w[u][2 * v + 1] = t.y; }
         median25_block2x2(w, mb);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dy = k >> 1, dx = k & 1;
-            float g = G[c + (2 + dy) * L::AW + 2 + dx];
-            float r1 = mr[k] + g, b1 = mb[k] + g;
-            int o = (ly + dy) * L::BW + lx + dx;
-            ER[o] = g - r1; EB[o] = g - b1;
-            int ty = ly + dy - 2, tx = lx + dx - 2;
-            if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { RP[ty * TW + tx] = r1; BP[ty * TW + tx] = b1; }
+        for (int dy = 0; dy < 2; ++dy) {
+            const F2 g2 = *(const F2*)(G + c + (2 + dy) * L::AW + 2);
+            F2 r1, b1, er, eb;
+            r1.x = mr[2 * dy] + g2.x; r1.y = mr[2 * dy + 1] + g2.y;
+            b1.x = mb[2 * dy] + g2.x; b1.y = mb[2 * dy + 1] + g2.y;
+            er.x = g2.x - r1.x; er.y = g2.y - r1.y; eb.x = g2.x - b1.x; eb.y = g2.y - b1.y;
+            const int o = (ly + dy) * L::BW + lx;
+            *(F2*)(ER + o) = er; *(F2*)(EB + o) = eb;
+            const int ty = ly + dy - 2, tx = lx - 2;         // even tx: the pair is inside the tile or outside as a whole
+            if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { *(F2*)(RP + ty * TW + tx) = r1; *(F2*)(BP + ty * TW + tx) = b1; }
         }
     }
 }
@@ -151,14 +155,26 @@ PYSP_D void median_phase_c(const MedianParams& p, char* __restrict__ smem, int t
         }
         float w[6][6], mr[4], mb[4];
 #pragma unroll
-        for (int u = 0; u < 6; ++u)
+        for (int u = 0; u < 6; ++u) {
+            if (EDGE) {
 #pragma unroll
-            for (int v = 0; v < 6; ++v) w[u][v] = ER[ry[u] * L::BW + rx[v]];
+                for (int v = 0; v < 6; ++v) w[u][v] = ER[ry[u] * L::BW + rx[v]];
+            } else {                                        // tx and BW are even: three aligned pairs per window row
+#pragma unroll
+                for (int v = 0; v < 3; ++v) { const F2 t = ((const F2*)(ER + ry[u] * L::BW + tx))[v]; w[u][2 * v] = t.x; w[u][2 * v + 1] = t.y; }
+            }
+        }
         median25_block2x2(w, mr);
 #pragma unroll
-        for (int u = 0; u < 6; ++u)
+        for (int u = 0; u < 6; ++u) {
+            if (EDGE) {
 #pragma unroll
-            for (int v = 0; v < 6; ++v) w[u][v] = EB[ry[u] * L::BW + rx[v]];
+                for (int v = 0; v < 6; ++v) w[u][v] = EB[ry[u] * L::BW + rx[v]];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 3; ++v) { const F2 t = ((const F2*)(EB + ry[u] * L::BW + tx))[v]; w[u][2 * v] = t.x; w[u][2 * v + 1] = t.y; }
+            }
+        }
         median25_block2x2(w, mb);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
