@@ -27,12 +27,17 @@ namespace pysp {
 template <int TW_, int TH_>
 struct SelectTile {
     static constexpr int TW = TW_, TH = TH_;
-    // Raw input box: the stencil needs tile + 6 px; horizontally the box starts 8 px left of the tile because a
-    // TMA tile load needs its inner coordinate to be a multiple of 16 bytes (8 u16 / 4 f32; TW % 8 == 0).
-    static constexpr int HX = 8, HY = 6;
-    static constexpr int BOXW = TW + 2 * HX, BOXH = TH + 2 * HY;
-    static constexpr int QW = BOXW / 2, QH = BOXH / 2;             // quarter planes incl. the halo quads
+    // Raw input box: the stencil needs tile + 6 px.  A TMA tile load needs its inner coordinate to be a multiple of 16
+    // bytes (8 u16 / 4 f32), so the box starts box_hx(tile_x) >= 6 px left of the tile: 8 px when the tile origin is a
+    // multiple of 8, else 12 px (tiles whose width is 4 mod 8, e.g. 60: every other tile).  The quarter planes keep
+    // exactly the 3-quad halo, so only phase 0 sees the variable margin.
+    static constexpr int HY = 6;
+    static constexpr bool WIDE = (TW % 8) != 0;
+    static constexpr int BOXW = TW + (WIDE ? 20 : 16), BOXH = TH + 2 * HY;
+    static constexpr int JX = 3, IY = HY / 2;                      // quarter index of the tile's first quad in the planes
+    static constexpr int QW = TW / 2 + 2 * JX, QH = BOXH / 2;      // quarter planes incl. the halo quads
     static constexpr int QN = QW * QH;
+    PYSP_HD static int box_hx(int tile_x) { return (WIDE && ((tile_x * TW) & 7)) ? 12 : 8; }
     static constexpr int LW = TW + 4, LH = TH + 4;                 // Lab region (tile + 2)
     static constexpr int CW = TW + 2, CH = TH + 2;                 // count region (tile + 1)
     // quarter planes (float): mosaic R,G1,G2,B ; H/V green at R and B ; H/V colour difference at R and B
@@ -48,7 +53,7 @@ struct SelectTile {
     static constexpr int SMEM_BYTES = align128(OFF_CAND + 4 * TH * TW * 4);
     static constexpr int OFF_OUT = OFF_LABL;       // [3][TH][TW] f32 output tile: aliases Lab (dead after phase 3)
     static constexpr int OFF_CNT = OFF_Q + P_DHR * QN * 4;   // [CH][CW] u16 (H | V << 8): aliases the D planes (dead after phase 2)
-    static_assert(TW % 8 == 0 && TH % 2 == 0, "tile must be quad aligned and start on 16-byte columns");
+    static_assert(TW % 4 == 0 && TH % 2 == 0 && BOXW % 8 == 0, "tile must be quad aligned and its box 16-byte granular");
     static_assert(3 * ((TH * TW * 4 + 127) / 128 * 128) <= 4 * LH * LW * 4, "output tile must fit in the Lab region");
     static_assert(CH * CW * 2 <= 4 * QN * 4, "count plane must fit in the D planes");
 };
@@ -61,7 +66,7 @@ struct OutPlane { static constexpr int FLOATS = (TH * TW * 4 + 127) / 128 * 32; 
 template <int TW, int TH>
 PYSP_HD void select_input_box(const SelectParams& p, int tile_x, int tile_y, int* bx, int* by) {
     typedef SelectTile<TW, TH> L;
-    const int x0 = tile_x * TW - L::HX, y0 = p.y_begin + tile_y * TH - L::HY;  // logical
+    const int x0 = tile_x * TW - L::box_hx(tile_x), y0 = p.y_begin + tile_y * TH - L::HY;  // logical
     *bx = p.g.flip_x ? p.g.W - (x0 + L::BOXW) : x0;
     *by = (p.g.flip_y ? p.g.H - (y0 + L::BOXH) : y0) - p.in_row0;
 }
@@ -226,19 +231,23 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
     typedef SelectTile<TW, TH> L;
     constexpr int QW = L::QW, QN = L::QN;
     const int H = p.g.H, W = p.g.W;
-    const int bx0 = tile_x * TW - L::HX, by0 = p.y_begin + tile_y * TH - L::HY;   // logical origin of the box
+    const int hx = L::box_hx(tile_x);
+    const int bx0 = tile_x * TW - hx, by0 = p.y_begin + tile_y * TH - L::HY;   // logical origin of the box
+    const int sh = hx - 2 * L::JX;                            // box column of plane column 0 (2 or 6: even)
     float* Q = (float*)(smem + L::OFF_Q);
     const void* stage = smem + L::OFF_STAGE;
     const int flipmask = (p.g.flip_y << 1) | p.g.flip_x;      // stored CFA position of logical position k is k ^ flipmask
+    constexpr int BW2 = L::BOXW / 2;                          // site pairs per box row
     PYSP_ITEMS(it, QN) {
         int qy = it / QW, qx = it - qy * QW;
         float v[4];
         if (!EDGE) {
             // the two sites of a mosaic row are adjacent in the staging box (also when mirrored): one 32/64-bit load
             const int r0 = p.g.flip_y ? L::BOXH - 1 - 2 * qy : 2 * qy, r1 = p.g.flip_y ? r0 - 1 : r0 + 1;
-            const int cp = p.g.flip_x ? QW - 1 - qx : qx;
+            const int lp = qx + (sh >> 1);                    // logical pair index in the box row
+            const int cp = p.g.flip_x ? BW2 - 1 - lp : lp;
             if (p.in_kind == IN_U16) {
-                uint32_t w0 = ((const uint32_t*)stage)[r0 * QW + cp], w1 = ((const uint32_t*)stage)[r1 * QW + cp];
+                uint32_t w0 = ((const uint32_t*)stage)[r0 * BW2 + cp], w1 = ((const uint32_t*)stage)[r1 * BW2 + cp];
                 if (p.g.flip_x) { w0 = (w0 >> 16) | (w0 << 16); w1 = (w1 >> 16) | (w1 << 16); }
                 v[0] = normalize_site(p, w0 & 0xFFFFu, 0 ^ flipmask);
                 v[1] = normalize_site(p, w0 >> 16, 1 ^ flipmask);
@@ -246,8 +255,8 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
                 v[3] = normalize_site(p, w1 >> 16, 3 ^ flipmask);
             } else {
                 const float* sf = (const float*)stage;
-                float a0 = sf[(r0 * QW + cp) * 2], a1 = sf[(r0 * QW + cp) * 2 + 1];
-                float b0 = sf[(r1 * QW + cp) * 2], b1 = sf[(r1 * QW + cp) * 2 + 1];
+                float a0 = sf[(r0 * BW2 + cp) * 2], a1 = sf[(r0 * BW2 + cp) * 2 + 1];
+                float b0 = sf[(r1 * BW2 + cp) * 2], b1 = sf[(r1 * BW2 + cp) * 2 + 1];
                 v[0] = p.g.flip_x ? a1 : a0; v[1] = p.g.flip_x ? a0 : a1;
                 v[2] = p.g.flip_x ? b1 : b0; v[3] = p.g.flip_x ? b0 : b1;
             }
@@ -255,7 +264,7 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 // phase-preserving clamp (ahd.py:77-80): the clamped site is always inside the same box
-                int y = phase_clamp(by0 + 2 * qy + (k >> 1), H), x = phase_clamp(bx0 + 2 * qx + (k & 1), W);
+                int y = phase_clamp(by0 + 2 * qy + (k >> 1), H), x = phase_clamp(bx0 + sh + 2 * qx + (k & 1), W);
                 int ly = y - by0, lx = x - bx0;
                 int si = (p.g.flip_y ? L::BOXH - 1 - ly : ly) * L::BOXW + (p.g.flip_x ? L::BOXW - 1 - lx : lx);
                 v[k] = p.in_kind == IN_U16 ? normalize_site(p, ((const uint16_t*)stage)[si], k ^ flipmask)
@@ -279,7 +288,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     const int H = p.g.H, W = p.g.W;
     const int hq = H >> 1, wq = W >> 1;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;     // logical origin of the output tile (even)
-    constexpr int JX = L::HX / 2, IY = L::HY / 2;                 // local quarter index of the tile's first quad
+    constexpr int JX = L::JX, IY = L::IY;                         // local quarter index of the tile's first quad
     const int qx0 = (x0 >> 1) - JX, qy0 = (y0 >> 1) - IY;         // quarter-plane origin
     float* Q = (float*)(smem + L::OFF_Q);
     float* labL = (float*)(smem + L::OFF_LABL);

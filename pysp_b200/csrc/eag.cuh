@@ -25,7 +25,7 @@ PYSP_D void eag_phases(const SelectParams& p, char* __restrict__ smem, int tile_
     const int H = p.g.H, W = p.g.W;
     const int hq = H >> 1, wq = W >> 1;
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
-    constexpr int JX = L::HX / 2, IY = L::HY / 2;
+    constexpr int JX = L::JX, IY = L::IY;
     const int qx0 = (x0 >> 1) - JX, qy0 = (y0 >> 1) - IY;
     float* Q = (float*)(smem + L::OFF_Q);
     float* out = (float*)(smem + L::OFF_OUT);

@@ -26,10 +26,10 @@ namespace pysp {
 
 // tile sizes (compile-time; the -D overrides exist for tools/kbench.py A/B builds)
 #ifndef PYSP_K1_TW
-#define PYSP_K1_TW 56
+#define PYSP_K1_TW 60
 #endif
 #ifndef PYSP_K1_TH
-#define PYSP_K1_TH 30
+#define PYSP_K1_TH 28
 #endif
 #ifndef PYSP_K2_TW
 #define PYSP_K2_TW 60

@@ -72,14 +72,15 @@ static void run_chain(const DevelopPlan& plan) {
 }
 
 extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
-    // tile sizes are compile-time in the kernels; the emulation instantiates the product's K1 tile (56x30) and a small
+    // tile sizes are compile-time in the kernels; the emulation instantiates the product's K1 tile (60x28) and a small
     // one (16x8) that puts many tile seams and partial tiles into small test frames
     DevelopPlan plan;
     int rc = plan_develop(a, tw, th, tw, th, &plan, g_err, sizeof(g_err));
     if (rc) return rc;
-    if (tw == 56 && th == 28) run_chain<56, 28>(plan);
-    else if (tw == 56 && th == 30) run_chain<56, 30>(plan);
+    if (tw == 60 && th == 28) run_chain<60, 28>(plan);        // the product's K1 / K2 tile
+    else if (tw == 56 && th == 30) run_chain<56, 30>(plan);   // a box with the fixed 8-px margin (tile width 0 mod 8)
     else if (tw == 16 && th == 8) run_chain<16, 8>(plan);
+    else if (tw == 20 && th == 8) run_chain<20, 8>(plan);     // tile width 4 mod 8: box margin alternates 8 / 12 px
     else {
         snprintf(g_err, sizeof(g_err), "emu_develop: tile %dx%d not instantiated", tw, th);
         return PYSP_ERR_INVALID;
