@@ -444,8 +444,8 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     // both ends (dL changes sign, dC^2 does not): 26 pair distances per block and direction instead of 32.
     {
         constexpr int BW = L::CW / 2, BH = L::CH / 2;
-        PYSP_ITEMS(it, BW * BH) {
-            int by = it / BW, bx = it - by * BW;
+        static_assert(BW <= 32, "phase 3 maps one row of blocks to a warp");
+        PYSP_ROW_ITEMS32(by, bx, BH, BW) {
             int cy = 2 * by, cx = 2 * bx;                 // count-region coords of the block's top-left pixel
             int fy = y0 - 1 + cy, fx = x0 - 1 + cx;       // frame coords
             // Lab-region local coords of the 4x4 window (edge-duplicated at the frame border, ahd.py:64)
@@ -543,8 +543,8 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
     // Window sums stay below 256 per byte (9 x 9), so plain 32-bit adds sum four byte counters at once.
     {
         constexpr int OW = TW / 2, OH = TH / 2;
-        PYSP_ITEMS(it, OW * OH) {
-            int oy = it / OW, ox = it - oy * OW;
+        static_assert(OW <= 32, "phase 4 maps one row of quads to a warp");
+        PYSP_ROW_ITEMS32(oy, ox, OH, OW) {
             int ty = 2 * oy, tx = 2 * ox;                 // tile coords of the quad
             int fy = y0 + ty, fx = x0 + tx;
             if (EDGE) { if (fy >= H || fx >= W) continue; }       // partial tile (even dims: whole quad in or out)

@@ -20,6 +20,9 @@
 #define PYSP_NOINLINE inline
 #define PYSP_SYNC() ((void)0)
 #define PYSP_ITEMS(var, n) for (int var = 0; var < (n); ++var)
+#define PYSP_ROW_ITEMS32(row, col, nrows, ncols)            \
+    for (int row = 0; row < (nrows); ++row)                 \
+        for (int col = 0; col < (ncols); ++col)
 static inline float pysp_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t pysp_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 template <typename T> static inline T pysp_ldg(const T* p) { return *p; }
@@ -31,6 +34,12 @@ template <typename T> static inline T pysp_ldg(const T* p) { return *p; }
 #define PYSP_NOINLINE __device__ __noinline__
 #define PYSP_SYNC() __syncthreads()
 #define PYSP_ITEMS(var, n) for (int var = threadIdx.x; var < (n); var += blockDim.x)
+// Work items on an nrows x ncols grid (ncols <= 32), one grid row per warp pass: the lanes of a warp never straddle two
+// rows, so unit-stride shared-memory accesses of a row stay free of bank conflicts (a flat item index wraps mid-warp and
+// costs a second wavefront on every access).  `continue` in the body skips the item.
+#define PYSP_ROW_ITEMS32(row, col, nrows, ncols)                                                    \
+    for (int it_ = threadIdx.x; it_ < (nrows) * 32; it_ += blockDim.x)                              \
+        for (int row = it_ >> 5, col = it_ & 31, once_ = 1; once_ && col < (ncols); once_ = 0)
 __device__ __forceinline__ float pysp_as_float(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t pysp_as_uint(float f) { return __float_as_uint(f); }
 template <typename T> __device__ __forceinline__ T pysp_ldg(const T* p) { return __ldg(p); }
