@@ -25,10 +25,10 @@ static char g_err[512];
 
 extern "C" const char* emu_last_error(void) { return g_err; }
 
-template <int TW, int TH>
+template <int TW, int TH, int TW2 = TW, int TH2 = TH>
 static void run_chain(const DevelopPlan& plan) {
     typedef SelectTile<TW, TH> LS;
-    typedef MedianTile<TW, TH> LM;
+    typedef MedianTile<TW2, TH2> LM;
     std::vector<float> buf((LS::SMEM_BYTES > LM::SMEM_BYTES ? LS::SMEM_BYTES : LM::SMEM_BYTES) / 4 + 64);
     char* smem = (char*)buf.data();
     auto poison = [&]() { for (size_t i = 0; i < buf.size(); ++i) buf[i] = __builtin_nanf(""); };
@@ -56,28 +56,29 @@ static void run_chain(const DevelopPlan& plan) {
         for (int t = 0; t < p.n_tiles; ++t) {
             int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
             poison();
-            const int bx = tx * TW - 4, by = p.y_begin + ty * TH - 4 - p.in_row0;
+            const int bx = tx * TW2 - 4, by = p.y_begin + ty * TH2 - 4 - p.in_row0;
             for (int k = 0; k < 3; ++k) box_load_generic(smem + LM::OFF_IN + k * LM::PLANE_BYTES, p.in[k], bx, by, LM::AW, LM::AH);
-            if (median_tile_is_edge<TW, TH>(p, tx, ty)) {
-                median_fix_border<TW, TH>(p, smem, tx, ty);
-                median_phase_b<TW, TH, true>(p, smem, tx, ty);
-                median_phase_c<TW, TH, true>(p, smem, tx, ty);
+            if (median_tile_is_edge<TW2, TH2>(p, tx, ty)) {
+                median_fix_border<TW2, TH2>(p, smem, tx, ty);
+                median_phase_b<TW2, TH2, true>(p, smem, tx, ty);
+                median_phase_c<TW2, TH2, true>(p, smem, tx, ty);
             } else {
-                median_phase_b<TW, TH, false>(p, smem, tx, ty);
-                median_phase_c<TW, TH, false>(p, smem, tx, ty);
+                median_phase_b<TW2, TH2, false>(p, smem, tx, ty);
+                median_phase_c<TW2, TH2, false>(p, smem, tx, ty);
             }
-            store_tile_generic<TW, TH>((const float*)(smem + LM::OFF_OUT), p.st, p.g, tx * TW, p.y_begin + ty * TH);
+            store_tile_generic<TW2, TH2>((const float*)(smem + LM::OFF_OUT), p.st, p.g, tx * TW2, p.y_begin + ty * TH2);
         }
     }
 }
 
 extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
-    // tile sizes are compile-time in the kernels; the emulation instantiates the product's K1 tile (60x28) and a small
+    // tile sizes are compile-time in the kernels; the emulation instantiates the product's tiles (K1 60x28, K2 60x60) and a small
     // one (16x8) that puts many tile seams and partial tiles into small test frames
     DevelopPlan plan;
-    int rc = plan_develop(a, tw, th, tw, th, &plan, g_err, sizeof(g_err));
+    const bool product = tw == 60 && th == 28;                // the product's tiles: K1 60x28, K2 60x60
+    int rc = plan_develop(a, tw, th, tw, product ? 60 : th, &plan, g_err, sizeof(g_err));
     if (rc) return rc;
-    if (tw == 60 && th == 28) run_chain<60, 28>(plan);        // the product's K1 / K2 tile
+    if (product) run_chain<60, 28, 60, 60>(plan);
     else if (tw == 56 && th == 30) run_chain<56, 30>(plan);   // a box with the fixed 8-px margin (tile width 0 mod 8)
     else if (tw == 16 && th == 8) run_chain<16, 8>(plan);
     else if (tw == 20 && th == 8) run_chain<20, 8>(plan);     // tile width 4 mod 8: box margin alternates 8 / 12 px
