@@ -116,10 +116,17 @@ __global__ void __launch_bounds__(256) leaf_sum_kernel(const float* mosaic, long
     }
 }
 
-// one block = one plane: combine the leaves in the order of NumPy's recursion, then mean = sum / float32(n)
-__global__ void __launch_bounds__(1024) tree_sum_kernel(PlaneSumTables t, float n_f32, float* mean) {
+// one wide level of the recursion tree (nodes [a, b) are independent), all four planes: blockIdx.y = plane
+__global__ void __launch_bounds__(256) tree_level_kernel(PlaneSumTables t, int a, int b) {
+    float* val = t.val + (long long)blockIdx.y * (t.n_leaves + t.n_nodes);
+    for (int k = a + blockIdx.x * blockDim.x + threadIdx.x; k < b; k += gridDim.x * blockDim.x)
+        val[t.n_leaves + k] = val[t.node_l[k]] + val[t.node_r[k]];
+}
+
+// one block = one plane: combine the remaining (narrow) levels in the order of NumPy's recursion, then mean = sum / float32(n)
+__global__ void __launch_bounds__(1024) tree_sum_kernel(PlaneSumTables t, int first_group, float n_f32, float* mean) {
     float* val = t.val + (long long)blockIdx.x * (t.n_leaves + t.n_nodes);
-    for (int g = 0; g < t.n_groups; ++g) {
+    for (int g = first_group; g < t.n_groups; ++g) {
         const int a = t.group_start[g], b = t.group_start[g + 1];
         for (int k = a + threadIdx.x; k < b; k += blockDim.x) val[t.n_leaves + k] = val[t.node_l[k]] + val[t.node_r[k]];
         __syncthreads();

@@ -646,7 +646,16 @@ int launch_plane_means(const float* mosaic, long long pitch, int H, int W, char*
     int rc = check_launch("leaf_sum_kernel");
     if (rc) return rc;
     const long long n = (long long)(H / 2) * (W / 2);
-    tree_sum_kernel<<<4, 1024, 0, stream>>>(t, (float)n, (float*)(ws + lay.off_mean));
+    // wide levels of the tree run on the whole GPU, the narrow top of the tree in one block per plane
+    int g0 = 0;
+    for (; g0 < ng; ++g0) {
+        const int a = pl.group_start[g0], b = pl.group_start[g0 + 1];
+        if (b - a < 4096) break;
+        tree_level_kernel<<<dim3((unsigned)((b - a + 255) / 256), 4), 256, 0, stream>>>(t, a, b);
+        rc = check_launch("tree_level_kernel");
+        if (rc) return rc;
+    }
+    tree_sum_kernel<<<4, 1024, 0, stream>>>(t, g0, (float)n, (float*)(ws + lay.off_mean));
     return check_launch("tree_sum_kernel");
 }
 }  // namespace
