@@ -408,9 +408,30 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 // Lab of the metric image, kept for the tile + 2 px
                 float* oL = labL + dir * (L::LH * L::LW);
                 uint32_t* oAB = labAB + dir * (L::LH * L::LW);
+                // software pipeline over the four pixels: the table loads of pixel k + 1 are issued before pixel k is
+                // interpolated (ptxas otherwise runs the pixels strictly one after the other)
                 LabQ q[4];
+                {
+                    float m3[3], luma[4];
+                    LabKey key[2];
+                    uint4 e[2][4];
+                    metric_rgb(p.c, Rc[0], Gc[0], Bc[0], m3, &luma[0]);
+                    key[0] = lab_key(p.lut, m3[0], m3[1], m3[2]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = metric_lab(p.c, p.lut, Rc[k], Gc[k], Bc[k]);
+                    for (int c = 0; c < 4; ++c) e[0][c] = pysp_ldg(key[0].base + (c >> 1) * PYSP_LUT_NG * PYSP_LUT_NB + (c & 1) * PYSP_LUT_NB);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < 3) {
+                            metric_rgb(p.c, Rc[k + 1], Gc[k + 1], Bc[k + 1], m3, &luma[k + 1]);
+                            key[(k + 1) & 1] = lab_key(p.lut, m3[0], m3[1], m3[2]);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                e[(k + 1) & 1][c] = pysp_ldg(key[(k + 1) & 1].base + (c >> 1) * PYSP_LUT_NG * PYSP_LUT_NB + (c & 1) * PYSP_LUT_NB);
+                        }
+                        q[k] = lab_interp(key[k & 1], e[k & 1][0], e[k & 1][1], e[k & 1][2], e[k & 1][3]);
+                        if (p.c.hdr) q[k].L = luma[k];
+                    }
+                }
                 // the two pixels of a row leave as one 8-byte store (a 32-bit store per pixel has lane stride 2: two-way
                 // bank conflicts on every store)
 #pragma unroll

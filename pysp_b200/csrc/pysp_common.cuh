@@ -218,23 +218,27 @@ PYSP_HD uint32_t dot2_u16_u8(uint32_t pair16, uint32_t w8, uint32_t acc) {
 #endif
 }
 
-PYSP_HD LabQ lab_lookup(const uint4* __restrict__ lut, float r, float g, float b) {
+struct LabKey { const uint4* base; uint32_t sr, sg, sb; };        // first of the four table nodes + the three 4-bit fractions
+
+PYSP_HD LabKey lab_key(const uint4* __restrict__ lut, float r, float g, float b) {
     const uint32_t cr = quant14(r), cg = quant14(g), cb = quant14(b);
     const uint32_t tr = cr >> 9, tg = cg >> 9, tb = cb >> 9;
-    const uint32_t sr = (cr >> 5) & 15u, sg = (cg >> 5) & 15u, sb = (cb >> 5) & 15u;
-    const uint4* base = lut + (tr * PYSP_LUT_NG + tg) * PYSP_LUT_NB + tb;
-    const uint4 e00 = pysp_ldg(base);
-    const uint4 e01 = pysp_ldg(base + PYSP_LUT_NB);
-    const uint4 e10 = pysp_ldg(base + PYSP_LUT_NG * PYSP_LUT_NB);
-    const uint4 e11 = pysp_ldg(base + PYSP_LUT_NG * PYSP_LUT_NB + PYSP_LUT_NB);
+    LabKey k;
+    k.sr = (cr >> 5) & 15u; k.sg = (cg >> 5) & 15u; k.sb = (cb >> 5) & 15u;
+    k.base = lut + (tr * PYSP_LUT_NG + tg) * PYSP_LUT_NB + tb;
+    return k;
+}
+
+PYSP_HD LabQ lab_interp(const LabKey& k, const uint4& e00, const uint4& e01, const uint4& e10, const uint4& e11) {
+    const uint32_t sr = k.sr, sg = k.sg, sb = k.sb;
     const uint32_t wb = (16u - sb) | (sb << 8), wg0 = 16u - sg, wr0 = 16u - sr;
     uint32_t v[3];
-#define PYSP_CH(k, f)                                                                              \
+#define PYSP_CH(c, f)                                                                              \
     {                                                                                              \
         uint32_t p00 = dot2_u16_u8(e00.f, wb, 0u), p01 = dot2_u16_u8(e01.f, wb, 0u);               \
         uint32_t p10 = dot2_u16_u8(e10.f, wb, 0u), p11 = dot2_u16_u8(e11.f, wb, 0u);               \
         uint32_t q0 = p00 * wg0 + p01 * sg, q1 = p10 * wg0 + p11 * sg;                             \
-        v[k] = (q0 * wr0 + q1 * sr + 2048u) >> 12;                                                 \
+        v[c] = (q0 * wr0 + q1 * sr + 2048u) >> 12;                                                 \
     }
     PYSP_CH(0, x) PYSP_CH(1, y) PYSP_CH(2, z)
 #undef PYSP_CH
@@ -242,6 +246,15 @@ PYSP_HD LabQ lab_lookup(const uint4* __restrict__ lut, float r, float g, float b
     q.L = (pysp_as_float(0x4B000000u | v[0]) - 8388608.0f) * (100.0f / 16384.0f);
     q.ab = v[1] | (v[2] << 16);
     return q;
+}
+
+PYSP_HD LabQ lab_lookup(const uint4* __restrict__ lut, float r, float g, float b) {
+    const LabKey k = lab_key(lut, r, g, b);
+    const uint4 e00 = pysp_ldg(k.base);
+    const uint4 e01 = pysp_ldg(k.base + PYSP_LUT_NB);
+    const uint4 e10 = pysp_ldg(k.base + PYSP_LUT_NG * PYSP_LUT_NB);
+    const uint4 e11 = pysp_ldg(k.base + PYSP_LUT_NG * PYSP_LUT_NB + PYSP_LUT_NB);
+    return lab_interp(k, e00, e01, e10, e11);
 }
 
 // integer-valued float from a 16-bit field, offset by 2^23 (differences of two such values are exact)
@@ -278,19 +291,28 @@ PYSP_HD uint32_t pass_ge(float dl, float neg_epsl, float d2, float epsc) {
 #endif
 }
 
-// debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
-PYSP_HD LabQ metric_lab(const ColorParams& c, const uint4* __restrict__ lut, float r, float g, float b) {
-    float c0 = r * c.wb[0], c1 = g * c.wb[1], c2 = b * c.wb[2];        // WB applied a 2nd time (ahd.py:46-48)
+// debayer/ahd.py:45-59 : candidate camera RGB -> the RGB that goes into the Lab conversion (and, for HDR frames, the luma
+// that replaces L): white balance a second time (ahd.py:46-48), float64 matrix, HDR tone curve x/(1+x) (ahd.py:52-57)
+PYSP_HD void metric_rgb(const ColorParams& c, float r, float g, float b, float* o, float* luma) {
+    float c0 = r * c.wb[0], c1 = g * c.wb[1], c2 = b * c.wb[2];
     float sr = dot3_f64(c.m_metric + 0, c0, c1, c2);
     float sg = dot3_f64(c.m_metric + 3, c0, c1, c2);
     float sb = dot3_f64(c.m_metric + 6, c0, c1, c2);
+    *luma = 0.0f;
     if (c.hdr) {
-        float luma = ((0.2126f * sr) + (0.7152f * sg)) + (0.0722f * sb);
-        LabQ q = lab_lookup(lut, sr / (1.0f + sr), sg / (1.0f + sg), sb / (1.0f + sb));
-        q.L = luma;
-        return q;
+        *luma = ((0.2126f * sr) + (0.7152f * sg)) + (0.0722f * sb);
+        sr = sr / (1.0f + sr); sg = sg / (1.0f + sg); sb = sb / (1.0f + sb);
     }
-    return lab_lookup(lut, sr, sg, sb);
+    o[0] = sr; o[1] = sg; o[2] = sb;
+}
+
+// debayer/ahd.py:45-62 : candidate camera RGB -> (L, a, b) of the homogeneity metric
+PYSP_HD LabQ metric_lab(const ColorParams& c, const uint4* __restrict__ lut, float r, float g, float b) {
+    float m[3], luma;
+    metric_rgb(c, r, g, b, m, &luma);
+    LabQ q = lab_lookup(lut, m[0], m[1], m[2]);
+    if (c.hdr) q.L = luma;
+    return q;
 }
 
 // ---- output epilogue ------------------------------------------------------------------------------------
