@@ -275,3 +275,32 @@ def test_lab_exhaustive_against_cv2(eng):
     rng = np.random.default_rng(2)
     x = rng.uniform(-0.3, 1.4, size=(1, 2_000_000, 3)).astype(np.float32)
     assert_bit_equal(eng.rgb_to_lab_cv2(torch.from_numpy(x).cuda()).cpu().numpy(), cv2.cvtColor(x, cv2.COLOR_RGB2LAB), "Lab")
+
+
+def test_full_size_properties(eng):
+    """Size-independent properties at BASELINE's full size (24 MP, configs 2 and 3):
+    (1) CFA equivalence -- a BGGR / GRBG / GBRG frame is the mirrored RGGB frame (image.py:143-152), so developing the
+        mirrored mosaic under that pattern must give the mirrored RGGB result, bit for bit (exercises the flipped TMA
+        boxes, the alternating 8/12-px box margin and the mirrored stores on every tile of a full frame);
+    (2) row bands with halo rows equal the whole frame at stages = 3 (halo 18 rows, config 3);
+    (3) the fused float32 output equals camera RGB -> pysp_cam_to_lin_srgb applied afterwards."""
+    H, W = 4000, 6000
+    raw = syn.scene(H, W, 11)
+    t = eng.to_device(raw)
+    kw = dict(black=syn.BLACK, white=syn.WHITE)
+    ref = eng.develop(t, WB, M, stages=1, **kw)
+    for pattern, dims in (("BGGR", (0, 1)), ("GRBG", (0,)), ("GBRG", (1,))):
+        # level order [TL,TR,BR,BL] is per stored position: equal levels here, so only the geometry is mirrored
+        flipped = torch.flip(t, dims=dims).contiguous()
+        out = eng.develop(flipped, WB, M, stages=1, pattern=pattern, **kw)
+        assert torch.equal(torch.flip(out, dims=dims).view(torch.int32), ref.view(torch.int32)), pattern
+        del out, flipped
+    whole = eng.develop(t, WB, M, stages=3, **kw)
+    halo = 6 + 4 * 3
+    for rb, re in ((0, 1334), (1334, 2666), (2666, 4000)):
+        r0, r1 = max(0, rb - halo), min(H, re + halo)
+        band = eng.develop(t[r0:r1].contiguous(), WB, M, stages=3, rows=(rb, re), frame_height=H, in_row0=r0, **kw)
+        assert torch.equal(band.view(torch.int32), whole[rb:re].view(torch.int32)), (rb, re)
+        del band
+    cam = eng.develop(t, WB, M, stages=1, out="cam", **kw)
+    assert torch.equal(eng.cam_to_rgb(cam, M, clip=True).view(torch.int32), ref.view(torch.int32))
