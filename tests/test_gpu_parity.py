@@ -304,3 +304,34 @@ def test_full_size_properties(eng):
         del band
     cam = eng.develop(t, WB, M, stages=1, out="cam", **kw)
     assert torch.equal(eng.cam_to_rgb(cam, M, clip=True).view(torch.int32), ref.view(torch.int32))
+
+
+def test_hdr_brackets_full_size(eng):
+    """BASELINE config 4 at full size: five 24 MP brackets fused in raw space (raw_hdr.py:108-148) and developed with the
+    HDR branch of the homogeneity metric (debayer/ahd.py:52-59).  The fuse is point-wise, so its result on sampled windows
+    equals the oracle on the cropped brackets exactly; the develop is checked on the same windows with a margin."""
+    from pysp_b200.raw_hdr import fusion_constants
+    H, W, margin = 4000, 6000, 16
+    base = (syn.scene(H, W, 5, noise=0).astype(np.float32) - np.float32(512.0)) / np.float32(16383.0)
+    evs = [8.0, 9.0, 10.0, 11.0, 12.0]
+    brackets = []
+    for k in range(5):
+        n = np.random.default_rng(k).normal(0, 30.0 / 16383.0, size=base.shape).astype(np.float32)
+        brackets.append(np.clip(base * np.float32(2.0 ** (2 - k)) + n, 0, 1).astype(np.float32))
+    tev, offs, bias = fusion_constants(evs, WB)
+    fused, cnt = eng.fuse_exposures([eng.to_device(b) for b in brackets], offs, bias, int(np.argmax(offs)))
+    out = eng.develop(fused, WB, M, stages=1, hdr=True)
+    torch.cuda.synchronize()
+    for (y, x) in [(0, 0), (H - 200, W - 200), (1000, 3000), (3000, 200)]:
+        y0, y1, x0, x1 = max(0, y - margin), min(H, y + 200 + margin), max(0, x - margin), min(W, x + 200 + margin)
+        f_ref, c_ref, _, _ = sp.fuse_exposures([b[y0:y1, x0:x1] for b in brackets], evs, WB)
+        assert_bit_equal(fused[y0:y1, x0:x1].cpu().numpy(), f_ref, "fused mosaic window (%d,%d)" % (y, x))
+        assert np.array_equal(cnt[y0:y1, x0:x1].cpu().numpy(), c_ref)
+        cam = sp.ahd_demosaic(f_ref, WB, M, 1, hdr=True)
+        lin = sp.to_lin_srgb(cam, M)
+        cy0 = 0 if y0 == 0 else margin
+        cx0 = 0 if x0 == 0 else margin
+        cy1 = (y1 - y0) if y1 == H else (y1 - y0 - margin)
+        cx1 = (x1 - x0) if x1 == W else (x1 - x0 - margin)
+        assert_bit_equal(out[y0 + cy0:y0 + cy1, x0 + cx0:x0 + cx1].cpu().numpy(), lin[cy0:cy1, cx0:cx1],
+                         "HDR develop window (%d,%d)" % (y, x))
