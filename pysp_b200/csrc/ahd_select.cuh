@@ -477,28 +477,37 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 wx[k] = EDGE ? clampi(fx - 1 + k, W) - (x0 - 2) : cx + k;
             }
             uint32_t res[4] = {0, 0, 0, 0};
+            // raw window loads of BOTH directions first (L as float, a|b packed), then one direction at a time: the loads
+            // of the vertical map are in flight while the horizontal one is evaluated
+            float rawl[2][4][4];
+            uint32_t rawab[2][4][4];
 #pragma unroll
             for (int dir = 0; dir < 2; ++dir) {
                 const float* iL = labL + dir * (L::LH * L::LW);
                 const uint32_t* iAB = labAB + dir * (L::LH * L::LW);
-                float wl[4][4], wa[4][4], wb[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    uint32_t ab[4];
                     if (EDGE) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) { int o = wy[a] * L::LW + wx[b]; wl[a][b] = iL[o]; ab[b] = iAB[o]; }
+                        for (int b = 0; b < 4; ++b) { int o = wy[a] * L::LW + wx[b]; rawl[dir][a][b] = iL[o]; rawab[dir][a][b] = iAB[o]; }
                     } else {
                         // cx and LW are even: the row is two aligned 8-byte pairs
                         const F2* rl = (const F2*)(iL + (cy + a) * L::LW + cx);
                         const U2* rab = (const U2*)(iAB + (cy + a) * L::LW + cx);
                         F2 l0 = rl[0], l1 = rl[1];
                         U2 q0 = rab[0], q1 = rab[1];
-                        wl[a][0] = l0.x; wl[a][1] = l0.y; wl[a][2] = l1.x; wl[a][3] = l1.y;
-                        ab[0] = q0.x; ab[1] = q0.y; ab[2] = q1.x; ab[3] = q1.y;
+                        rawl[dir][a][0] = l0.x; rawl[dir][a][1] = l0.y; rawl[dir][a][2] = l1.x; rawl[dir][a][3] = l1.y;
+                        rawab[dir][a][0] = q0.x; rawab[dir][a][1] = q0.y; rawab[dir][a][2] = q1.x; rawab[dir][a][3] = q1.y;
                     }
+                }
+            }
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) { wa[a][b] = ab_lo(ab[b]); wb[a][b] = ab_hi(ab[b]); }
+            for (int dir = 0; dir < 2; ++dir) {
+                float wl[4][4], wa[4][4], wb[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { wl[a][b] = rawl[dir][a][b]; wa[a][b] = ab_lo(rawab[dir][a][b]); wb[a][b] = ab_hi(rawab[dir][a][b]); }
                 }
                 // pair distances, first cell = the upper (then left) one: dL = L(second) - L(first)
                 float hl[4][3], h2[4][3], vl[3][4], v2[3][4], gl[3][3], g2[3][3], al[3][3], a2[3][3];
