@@ -95,7 +95,7 @@ def cpu_port(sample_hw, threads):
     from pysp_b200 import synthetic as syn
     cv2.setNumThreads(threads)
     cv2.setUseOptimized(True)
-    count_fn, kind = None, "port"
+    count_fn, kind = None, "port: NumPy/OpenCV restatement of the reference (oracle cv2 backend)"
     so_dir = os.path.join(ROOT, "oracle", "_ref")
     try:
         import importlib.machinery
@@ -108,7 +108,7 @@ def cpu_port(sample_hw, threads):
             mod = importlib.util.module_from_spec(spec)
             loader.exec_module(mod)
             count_fn = lambda lab, vertical: mod.build_map(np.ascontiguousarray(lab), 1, 3, bool(vertical))  # noqa: E731
-            kind = "port (NumPy/OpenCV restatement + the reference's own compiled count map)"
+            kind = "port: NumPy/OpenCV restatement of the reference + the reference's own compiled count map (oracle/_ref)"
     except Exception:
         count_fn = None
     raw = syn.scene(sample_hw[0], sample_hw[1], 0)
@@ -142,7 +142,7 @@ def run_reference(args, rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "QualityDemosaic.Best AHD (postprocess_stages=1) + WB + cam->lin sRGB, synthetic "
                                    "6000x4000 14-bit RGGB; CPU arm on a bounded crop", "stages": STAGES},
-            "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "port", "detail": kind, "sample": sample},
             "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -308,7 +308,8 @@ def main():
             once()
             best = min(once() for _ in range(2))
             line["cpu_baseline"] = {"value": CPU_SAMPLE[0] * CPU_SAMPLE[1] / best / 1e6, "unit": "Mpix/s", "cores": threads,
-                                    "kind": kind, "sample": "%dx%d crop of frame 0, best of 2 after 1 warm-up" % (
+                                    "kind": "port", "detail": kind,
+                                    "sample": "%dx%d crop of frame 0, best of 2 after 1 warm-up" % (
                                         CPU_SAMPLE[1], CPU_SAMPLE[0])}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
