@@ -1,5 +1,6 @@
+"""Small driver for ncu: flat-field correction, hot-pixel detection and raw-space fuse on one 24 MP frame (launch list / DRAM bytes)."""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 import numpy as np, torch
 from pysp_b200 import engine
 rng = np.random.default_rng(0)
