@@ -279,8 +279,9 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
 }
 
 // ---- phases 1..4 ---------------------------------------------------------------------------------------------
-// `before_out` is called by every thread after phase 3 and before the barrier that precedes the first write
-// to the output staging tile (the device pipeline waits there for the previous tile's TMA store).
+// `before_out` is called by every thread after phase 1 and before the barrier that precedes the first write to the Lab
+// planes, whose memory the output staging tile shares (the device pipeline waits there until the previous tile's TMA
+// store has read the staging tile).
 template <int TW, int TH, bool EDGE, typename BeforeOut>
 PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int tile_x, int tile_y, BeforeOut before_out) {
     typedef SelectTile<TW, TH> L;
@@ -322,6 +323,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
             Q[L::P_DHB * QN + c] = b - ghb; Q[L::P_DVB * QN + c] = b - gvb;
         }
     }
+    before_out();
     PYSP_SYNC();
     PYSP_PHASE_MARK(0, 2);
 
@@ -564,7 +566,6 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
             for (int a = 0; a < 2; ++a) *(uint32_t*)(cnt + (cy + a) * L::CW + cx) = res[2 * a] | (res[2 * a + 1] << 16);
         }
     }
-    before_out();
     PYSP_SYNC();
     PYSP_PHASE_MARK(0, 4);
 

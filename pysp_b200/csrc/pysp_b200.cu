@@ -134,8 +134,12 @@ ahd_select_kernel(const __grid_constant__ SelectParams p, const __grid_constant_
         PYSP_PHASE_MARK(0, 6);
         store_tile<K1_TW, K1_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K1_TW,
                                  p.y_begin + tile_y * K1_TH);
-        if (!p.tma_in && next < p.n_tiles) fetch(next);
-        __syncthreads();                                  // planes free for the next tile; generic store/load done
+        if (!p.tma_in) {                                  // generic load of the next box by the whole CTA: phase 0 reads it
+            if (next < p.n_tiles) fetch(next);
+            __syncthreads();
+        }
+        // (with TMA loads no barrier is needed here: phase 0 of the next tile only writes the native planes, which every
+        // thread has finished reading before the barrier above, and the staging tile is next written two barriers later)
         PYSP_PHASE_MARK(0, 7);
     }
     if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();
