@@ -335,3 +335,20 @@ def test_hdr_brackets_full_size(eng):
         cx1 = (x1 - x0) if x1 == W else (x1 - x0 - margin)
         assert_bit_equal(out[y0 + cy0:y0 + cy1, x0 + cx0:x0 + cx1].cpu().numpy(), lin[cy0:cy1, cx0:cx1],
                          "HDR develop window (%d,%d)" % (y, x))
+
+
+def test_repeatability_under_load(eng):
+    """The tile pipeline re-uses shared memory across phases and tiles (TMA store of tile t in flight while tile t+1 is
+    computed).  A hazard there would show up as run-to-run differences: 40 back-to-back 24 MP develops, alternating two
+    frames so that the persistent CTAs never see the same data twice in a row, must each reproduce their first result."""
+    H, W = 4000, 6000
+    frames = [eng.to_device(syn.scene(H, W, s)) for s in (21, 22)]
+    kw = dict(stages=1, black=syn.BLACK, white=syn.WHITE)
+    outs = [torch.empty((H, W, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+    sums = []
+    for i in range(40):
+        eng.develop(frames[i & 1], WB, M, out_tensor=outs[i & 1], **kw)
+        sums.append(outs[i & 1].view(torch.int32).to(torch.int64).sum())
+    torch.cuda.synchronize()
+    vals = [int(s.item()) for s in sums]
+    assert len(set(vals[0::2])) == 1 and len(set(vals[1::2])) == 1, vals
