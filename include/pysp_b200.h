@@ -81,6 +81,11 @@ typedef struct pysp_develop_args {
     const void* lab_lut;         /* device copy of the table packed by pysp_lab_lut_pack_host (Best only) */
     int32_t quality;             /* PYSP_QUALITY_BEST: debayer_ahd; PYSP_QUALITY_FAST: debayer_eag
                                     (debayer/edge_assisted_gaussian.py:188-201; stages and is_hdr are ignored) */
+    uint8_t* dir_map;            /* optional (NULL = none; Best only): the AHD direction choice `map_h < map_v`
+                                    (debayer/ahd.py:136-139), one byte per pixel, 1 = horizontal candidate taken;
+                                    [rows][width] for rows [out_row0, ...) of the frame as stored.  The reference never
+                                    returns this map; it is exported so that parity of the choice can be checked. */
+    int64_t dir_map_pitch_bytes;
 } pysp_develop_args;
 
 int pysp_develop(const pysp_develop_args* args, void* stream);

@@ -163,10 +163,12 @@ def mat3_f64(rgb, m):
 
 
 def lab_cv(rgb):
-    """cv2.cvtColor(float32, COLOR_RGB2LAB) restated; exact over all inputs
-    except NaN.  Returns float32 Lab."""
+    """cv2.cvtColor(float32, COLOR_RGB2LAB) restated.  Returns float32 Lab.
+    Non-finite input: cv2 4.13 (generic and optimised paths alike, probed) clamps with min/max whose NaN operand loses,
+    i.e. NaN -> 0, +inf -> 1, -inf -> 0; restated here so that frames with non-finite photosites are defined."""
     lut = lab_lut()
-    x = np.clip(rgb.astype(f32), f32(0), f32(1))
+    x = rgb.astype(f32)
+    x = np.clip(np.where(np.isnan(x), f32(0), x), f32(0), f32(1))
     c = np.rint(x * f32(16384.0)).astype(np.int32)          # cvRound: half to even
     t = c >> 9
     s = (c >> 5) & 15
@@ -388,8 +390,12 @@ def ahd_demosaic(sensor, wb, m_cam_to_srgb, stages=1, hdr=False, backend="spec",
     sum_h = be.box3(cnt_h)                                         # ahd.py:133-134
     sum_v = be.box3(cnt_v)
     pick_h = sum_h < sum_v                                         # ahd.py:136-145 (ties -> V)
-    sel = pick_h[..., None]
-    rgb = np.where(sel, np.dstack((r_h, g_h, b_h)), np.dstack((r_v, g_v, b_v))).astype(f32)
+    # ahd.py:139-145: a multiplicative blend, not a select -- h*c + v*(1-c) with c in {0, 1}.  For finite candidates it
+    # equals the chosen one; a non-finite value in the candidate that is NOT chosen still turns the pixel into NaN
+    # (inf * 0), and so does a non-finite native green (both candidates hold it).
+    comb = pick_h.astype(f32)[..., None]
+    with np.errstate(invalid="ignore"):
+        rgb = (np.dstack((r_h, g_h, b_h)).astype(f32) * comb + np.dstack((r_v, g_v, b_v)).astype(f32) * (1 - comb)).astype(f32)
     selected = rgb
     for _ in range(max(int(stages), 0)):                           # ahd.py:148-165
         rr, gg, bb = rgb[..., 0], rgb[..., 1], rgb[..., 2]

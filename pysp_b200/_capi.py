@@ -32,6 +32,7 @@ class DevelopArgs(C.Structure):
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
         ("lab_lut", C.c_void_p),
         ("quality", C.c_int32),
+        ("dir_map", C.c_void_p), ("dir_map_pitch_bytes", C.c_int64),
     ]
 
 
@@ -116,7 +117,7 @@ def check(rc, last_error=None):
 
 def fill_develop_args(height, width, pattern, in_kind, in_ptr, in_pitch, in_row0, in_rows, black, white, wb,
                       cam_to_srgb, stages, is_hdr, gamma, out_kind, out_ptr, out_pitch, out_row0, row_begin,
-                      row_end, scratch_ptr, scratch_bytes, lut_ptr, quality=0):
+                      row_end, scratch_ptr, scratch_bytes, lut_ptr, quality=0, dir_map_ptr=None, dir_map_pitch=0):
     a = DevelopArgs()
     a.height, a.width = int(height), int(width)
     if isinstance(pattern, str):
@@ -148,4 +149,6 @@ def fill_develop_args(height, width, pattern, in_kind, in_ptr, in_pitch, in_row0
     a.scratch_bytes = int(scratch_bytes)
     a.lab_lut = lut_ptr
     a.quality = int(quality)
+    a.dir_map = dir_map_ptr
+    a.dir_map_pitch_bytes = int(dir_map_pitch)
     return a

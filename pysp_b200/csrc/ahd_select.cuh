@@ -608,17 +608,27 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                 const uint32_t t[2] = {(s & 0xFFFFu) + (v0 >> 16), (s >> 16) + (v1 & 0xFFFFu)};
                 const F2* ch = (const F2*)(cand + (ty + a) * TW + tx);         // tx even: one 8-byte load per plane
                 const F2 rh = ch[0], bh = ch[TH * TW / 2], rv = ch[TH * TW], bv = ch[3 * TH * TW / 2];
+                // ahd.py:139-145 blends h*c + v*(1-c) with c in {0,1}: the chosen candidate plus 0 x the other one, so a
+                // non-finite value in the candidate NOT chosen (or in a native green, which both candidates hold) makes
+                // the pixel NaN.  For finite candidates the sum is the chosen value, bit for bit.
                 Rgb v[2];
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const int k = a * 2 + b;
                     const bool pick_h = (t[b] & 0xFFu) < (t[b] >> 8);          // sum_h < sum_v; ties -> V (ahd.py:139)
-                    v[b].r = pick_h ? (b ? rh.y : rh.x) : (b ? rv.y : rv.x);
-                    v[b].b = pick_h ? (b ? bh.y : bh.x) : (b ? bv.y : bv.x);
-                    if (k == 0) v[b].g = pick_h ? Q[L::P_GHR * QN + qi] : Q[L::P_GVR * QN + qi];
-                    else if (k == 1) v[b].g = Q[L::P_G1 * QN + qi];
-                    else if (k == 2) v[b].g = Q[L::P_G2 * QN + qi];
-                    else v[b].g = pick_h ? Q[L::P_GHB * QN + qi] : Q[L::P_GVB * QN + qi];
+                    if (p.dir_map) {                                           // optional export of the choice
+                        const int sy = p.g.flip_y ? H - 1 - (fy + a) : fy + a, sx = p.g.flip_x ? W - 1 - (fx + b) : fx + b;
+                        if (sy >= p.dir_rb && sy < p.dir_re) p.dir_map[(long long)(sy - p.dir_row0) * p.dir_pitch + sx] = pick_h ? 1 : 0;
+                    }
+                    const float r_h = b ? rh.y : rh.x, r_v = b ? rv.y : rv.x, b_h = b ? bh.y : bh.x, b_v = b ? bv.y : bv.x;
+                    float g_h, g_v;
+                    if (k == 0) { g_h = Q[L::P_GHR * QN + qi]; g_v = Q[L::P_GVR * QN + qi]; }
+                    else if (k == 1) g_h = g_v = Q[L::P_G1 * QN + qi];
+                    else if (k == 2) g_h = g_v = Q[L::P_G2 * QN + qi];
+                    else { g_h = Q[L::P_GHB * QN + qi]; g_v = Q[L::P_GVB * QN + qi]; }
+                    v[b].r = (pick_h ? r_h : r_v) + (pick_h ? r_v : r_h) * 0.0f;
+                    v[b].g = (pick_h ? g_h : g_v) + (pick_h ? g_v : g_h) * 0.0f;
+                    v[b].b = (pick_h ? b_h : b_v) + (pick_h ? b_v : b_h) * 0.0f;
                 }
                 stage_pixel_pair<TW, TH>(out, p.st, p.g, p.c, ty + a, tx, v[0], v[1]);
             }

@@ -9,18 +9,17 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/pysp_b200.h"
 #include "pysp_common.cuh"
 
 namespace pysp {
 
-#define PYSP_MAX_STAGES 16
-
 struct DevelopPlan {
     SelectParams select;
     int n_stages;
-    MedianParams median[PYSP_MAX_STAGES];
+    std::vector<MedianParams> median;      // one launch per postprocess stage (debayer/ahd.py:163-165: no upper limit)
 };
 
 static inline int plan_fail(char* err, size_t n, int code, const char* fmt, ...) {
@@ -103,8 +102,8 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         return plan_fail(err, errn, PYSP_ERR_UNSUPPORTED, "Quality mode not implemented: %d", a->quality);   // image.py:176
     // postprocess steps are "ignored unless using Best quality" (image.py:163)
     const int S = (a->quality == PYSP_QUALITY_BEST && a->stages > 0) ? a->stages : 0;      // debayer/ahd.py:163
-    if (S > PYSP_MAX_STAGES)
-        return plan_fail(err, errn, PYSP_ERR_UNSUPPORTED, "pysp_develop: at most %d postprocess stages", PYSP_MAX_STAGES);
+    if ((int64_t)8 * S > 0x3fffffff - H)
+        return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: %d postprocess stages overflow the row arithmetic", S);
     const int64_t esz = a->in_kind == PYSP_IN_U16 ? 2 : 4;
     if (a->in_pitch_bytes < W * esz || (a->in_pitch_bytes % esz) || ((uintptr_t)a->in % esz))
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad input pitch/alignment");
@@ -155,7 +154,9 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         st.plane_row0 = row0;
     };
 
-    memset(plan, 0, sizeof(*plan));
+    memset(&plan->select, 0, sizeof(plan->select));
+    plan->median.assign((size_t)S, MedianParams());
+    for (auto& mp : plan->median) memset(&mp, 0, sizeof(mp));
     SelectParams& sp = plan->select;
     sp.g = g; sp.c = c;
     sp.in_kind = a->in_kind;
@@ -170,6 +171,11 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     }
     sp.lut = (const uint4*)a->lab_lut;
     sp.algo = a->quality == PYSP_QUALITY_FAST ? ALGO_EAG : ALGO_AHD;
+    if (a->dir_map && sp.algo == ALGO_AHD) {
+        if (a->dir_map_pitch_bytes < W)
+            return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: dir_map pitch %lld is shorter than a row", (long long)a->dir_map_pitch_bytes);
+        sp.dir_map = a->dir_map; sp.dir_pitch = a->dir_map_pitch_bytes; sp.dir_row0 = a->out_row0; sp.dir_rb = rb; sp.dir_re = re;
+    }
     sp.y_begin = k1b; sp.y_end = k1e;
     sp.tiles_x = (W + tw1 - 1) / tw1;
     sp.n_tiles = sp.tiles_x * ((k1e - k1b + th1 - 1) / th1);

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) wb_kernel(WbParams p) {
             if (p.normalized) v = v * p.max_wb;
             v = __double2float_rn(__ddiv_rn((double)v, (double)p.wb[c]));
         } else {
-            v = fminf(fmaxf(v, 0.0f), 1.0f);
+            v = clip01(v);
         }
         p.out[i] = v;
     }

@@ -225,24 +225,26 @@ static int check_launch(const char* what) {
 
 // ---- optional per-kernel timing (bench only): CUDA events recorded on the launching stream ---------------
 #define PYSP_TIMING_SLOTS 4
-#define PYSP_TIMING_MAX 2048
+struct TimedEvents { cudaEvent_t a, b; int slot; };
 static std::mutex g_tmutex;
 static bool g_timing = false;
-static struct { cudaEvent_t a, b; int slot; } g_tev[PYSP_TIMING_MAX];
-static int g_tn = 0;
+static std::vector<TimedEvents> g_tev;      // one pair per launch since the last enable/collect; grows as needed
+static std::atomic<long long> g_tfail{0};   // launches whose events could not be created (reported by collect)
 
 struct TimedLaunch {     // records an event pair around one launch when timing is enabled
-    cudaStream_t s; int idx;
-    TimedLaunch(int slot, cudaStream_t stream) : s(stream), idx(-1) {
+    cudaStream_t s; cudaEvent_t b; bool on;
+    TimedLaunch(int slot, cudaStream_t stream) : s(stream), b(nullptr), on(false) {
         if (!g_timing) return;
+        TimedEvents e;
+        e.slot = slot;
+        if (cudaEventCreate(&e.a) != cudaSuccess) { g_tfail.fetch_add(1); return; }
+        if (cudaEventCreate(&e.b) != cudaSuccess) { cudaEventDestroy(e.a); g_tfail.fetch_add(1); return; }
+        cudaEventRecord(e.a, s);
+        b = e.b; on = true;
         std::lock_guard<std::mutex> lk(g_tmutex);
-        if (g_tn >= PYSP_TIMING_MAX) return;
-        idx = g_tn++;
-        g_tev[idx].slot = slot;
-        cudaEventCreate(&g_tev[idx].a); cudaEventCreate(&g_tev[idx].b);
-        cudaEventRecord(g_tev[idx].a, s);
+        g_tev.push_back(e);
     }
-    ~TimedLaunch() { if (idx >= 0) cudaEventRecord(g_tev[idx].b, s); }
+    ~TimedLaunch() { if (on) cudaEventRecord(b, s); }
 };
 
 static int ensure_device() {
@@ -266,24 +268,28 @@ int64_t pysp_kernel_launches(void) { return g_launches.load(); }
 
 void pysp_timing_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(g_tmutex);
-    for (int i = 0; i < g_tn; ++i) { cudaEventDestroy(g_tev[i].a); cudaEventDestroy(g_tev[i].b); }
-    g_tn = 0;
+    for (auto& e : g_tev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g_tev.clear();
+    g_tfail.store(0);
     g_timing = on != 0;
 }
 
 int pysp_timing_collect(double* total_ms, int64_t* launches) {
     std::lock_guard<std::mutex> lk(g_tmutex);
     for (int k = 0; k < PYSP_TIMING_SLOTS; ++k) { total_ms[k] = 0.0; launches[k] = 0; }
-    for (int i = 0; i < g_tn; ++i) {
-        cudaError_t e = cudaEventSynchronize(g_tev[i].b);
+    int rc = PYSP_OK;
+    for (auto& ev : g_tev) {
+        cudaError_t e = cudaEventSynchronize(ev.b);
         float ms = 0.f;
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g_tev[i].a, g_tev[i].b);
-        if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "pysp_timing_collect: %s", cudaGetErrorString(e));
-        total_ms[g_tev[i].slot] += ms; launches[g_tev[i].slot] += 1;
-        cudaEventDestroy(g_tev[i].a); cudaEventDestroy(g_tev[i].b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
+        if (e != cudaSuccess) rc = fail(PYSP_ERR_CUDA, "pysp_timing_collect: %s", cudaGetErrorString(e));
+        else { total_ms[ev.slot] += ms; launches[ev.slot] += 1; }
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
     }
-    g_tn = 0;
-    return PYSP_OK;
+    g_tev.clear();
+    const long long lost = g_tfail.exchange(0);
+    if (rc == PYSP_OK && lost) rc = fail(PYSP_ERR_CUDA, "pysp_timing_collect: %lld launches were not timed (event creation failed)", lost);
+    return rc;
 }
 
 // developer hook: per-phase SM clocks summed over CTAs (zeros unless built with -DPYSP_PHASE_CLOCKS); resets them
@@ -403,6 +409,14 @@ static int chain_setup(const ChainSetup** out) {
     return PYSP_OK;
 }
 
+// Test hook, read ONCE per process: PYSP_DISABLE_TMA bit 0 = loads, bit 1 = stores take the generic (non-TMA) path that
+// unaligned tensors take anyway, bit 2 = IEEE division instead of the verified reciprocal form.  tests/test_gpu_parity.py
+// sets it in a fresh process to prove those paths give the same bits.
+static int debug_path_bits() {
+    static const int bits = [] { const char* e = getenv("PYSP_DISABLE_TMA"); return e ? atoi(e) : 0; }();
+    return bits;
+}
+
 int pysp_develop(const pysp_develop_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DevelopPlan plan;
@@ -410,11 +424,9 @@ int pysp_develop(const pysp_develop_args* a, void* stream_) {
     if (rc) return rc;
     rc = ensure_device();
     if (rc) return rc;
-    if (const char* e = getenv("PYSP_DISABLE_TMA")) {     // test hook: bit 0 = loads, bit 1 = stores use the generic path,
-                                                          // bit 2 = IEEE division instead of the verified reciprocal form
-        const int bits = atoi(e);
-        if (bits & 1) { plan.select.tma_in = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].tma_in = 0; }
-        if (bits & 2) { plan.select.st.tma = 0; for (int s = 0; s < plan.n_stages; ++s) plan.median[s].st.tma = 0; }
+    if (const int bits = debug_path_bits()) {
+        if (bits & 1) { plan.select.tma_in = 0; for (auto& mp : plan.median) mp.tma_in = 0; }
+        if (bits & 2) { plan.select.st.tma = 0; for (auto& mp : plan.median) mp.st.tma = 0; }
         if (bits & 4) plan.select.fast_div = 0;
     }
     const int smem1 = SelectTile<K1_TW, K1_TH>::SMEM_BYTES, smem2 = MedianTile<K2_TW, K2_TH>::SMEM_BYTES;

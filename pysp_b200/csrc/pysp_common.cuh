@@ -126,6 +126,11 @@ struct SelectParams {    // K1: mosaic -> selected camera RGB
     StoreParams st;
     int y_begin, y_end;  // logical rows to produce (even)
     int tiles_x, n_tiles;
+    // optional export of the direction choice (one byte per pixel, stored orientation): rows [dir_rb, dir_re) of the
+    // frame as stored are written, map row 0 = stored row dir_row0
+    uint8_t* dir_map;
+    long long dir_pitch;
+    int dir_row0, dir_rb, dir_re;
 };
 
 struct MedianParams {    // K2: one postprocess stage (debayer/ahd.py:148-161)
@@ -166,7 +171,19 @@ PYSP_HD float dot3_f64(const double* m, float c0, float c1, float c2) {
 __device__ __forceinline__ float exp2f_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
-PYSP_HD float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+// np.clip(v, 0, 1) (colorize/transform.py:6-19): NaN stays NaN (max.NaN / min.NaN: one FMNMX each, as fminf/fmaxf)
+PYSP_HD float clip01(float v) {
+#ifdef __CUDA_ARCH__
+    float t, r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(t) : "f"(v));
+    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(t));
+    return r;
+#else
+    return v != v ? v : fminf(fmaxf(v, 0.0f), 1.0f);
+#endif
+}
+// cv2's clamp in front of the Lab quantisation: NaN -> 0, +inf -> 1, -inf -> 0 (probed on cv2 4.13, both code paths)
+PYSP_HD float sat01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
 // colorize/transform.py:98-99 in float32.  x^(1/2.4) = exp2(log2(x) / 2.4) with the hardware approximations (MUFU.LG2 /
 // MUFU.EX2): relative error of the curve about 1e-6, inside the 1e-4 the parity contract states for the gamma.
@@ -205,7 +222,7 @@ PYSP_HD uint32_t quant14(float v) {
 #ifdef __CUDA_ARCH__
     float y = fmaf(__saturatef(v), 16384.0f, 8388608.0f);
 #else
-    float y = fmaf(clip01(v), 16384.0f, 8388608.0f);
+    float y = fmaf(sat01(v), 16384.0f, 8388608.0f);
 #endif
     return pysp_as_uint(y) & 0x7FFFFFu;
 }

@@ -4,6 +4,7 @@ PyTorch is used only for device memory, streams and (elsewhere) torch.distribute
 the develop path happens in the CUDA kernels behind the C ABI.  There is no CPU path: calling into this
 module without a CUDA device raises.
 """
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -27,6 +28,20 @@ def require_cuda():
 def _stream_ptr(stream=None):
     s = stream if stream is not None else torch.cuda.current_stream()
     return s.cuda_stream
+
+
+@contextlib.contextmanager
+def _on(device, stream):
+    """Make `device` current and `stream` torch's current stream for the body of an entry point.  Every temporary and
+    output is then allocated by the caching allocator ON the stream the kernels are launched on, so a block that is
+    freed while kernels are still queued can only be handed out again behind them (the allocator orders re-use against
+    the allocation stream only)."""
+    with torch.cuda.device(device):
+        if stream is None:
+            yield
+        else:
+            with torch.cuda.stream(stream):
+                yield
 
 
 def lab_lut(device):
@@ -83,7 +98,7 @@ _OUT_KINDS = {"cam": _capi.OUT_CAM_F32, "lin": _capi.OUT_LIN_F32, "lin_f16": _ca
 
 def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white=None, hdr=False, gamma=False,
             out="lin", out_tensor=None, rows=None, frame_height=None, in_row0=0, out_row0=None, stream=None,
-            quality="best"):
+            quality="best", dir_map=None):
     """Run the fused develop chain on one frame (or one row band of it) that is resident on the GPU.
 
     mosaic      CUDA tensor [rows_held, W]: uint16/int16 sensor counts (normalisation fused, needs
@@ -91,6 +106,7 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
     rows        (row_begin, row_end) of the stored frame to produce; default the whole frame.
     frame_height / in_row0   when `mosaic` holds only rows [in_row0, in_row0+rows_held) of a taller frame.
     quality     "best" = AHD (debayer_ahd), "fast" = edge-assisted Gaussian (debayer_eag; stages/hdr ignored).
+    dir_map     optional CUDA uint8 tensor [>= row_end-out_row0, W]: receives the AHD direction choice (1 = horizontal).
     Returns a CUDA tensor [row_end-row_begin, W, 3] (float32, or float16 for out="lin_f16").
     """
     if quality not in ("best", "fast"):
@@ -103,8 +119,6 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
         raise ValueError("engine.develop: mosaic must be a CUDA tensor (use engine.to_device)")
     if mosaic.dim() != 2:
         raise ValueError("engine.develop: mosaic must be 2-D")
-    if mosaic.stride(1) != 1:
-        mosaic = mosaic.contiguous()
     held, W = mosaic.shape
     H = int(frame_height) if frame_height is not None else held
     if mosaic.dtype in (torch.uint16, torch.int16):
@@ -121,7 +135,12 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
     if out_row0 is None:
         out_row0 = rb
     dev = mosaic.device
-    with torch.cuda.device(dev):
+    if dir_map is not None and (not dir_map.is_cuda or dir_map.dtype != torch.uint8 or dir_map.dim() != 2
+                                or dir_map.shape[1] != W or dir_map.stride(1) != 1 or dir_map.shape[0] < re - out_row0):
+        raise ValueError("engine.develop: dir_map must be a CUDA uint8 tensor [rows, W]")
+    with _on(dev, stream):
+        if mosaic.stride(1) != 1:
+            mosaic = mosaic.contiguous()
         if out_tensor is None:
             out_tensor = torch.empty((re - out_row0, W, 3), dtype=odt, device=dev)
         elif (not out_tensor.is_cuda or out_tensor.dtype != odt or out_tensor.dim() != 3
@@ -136,7 +155,9 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
             black, white, wb, cam_to_srgb, stages, hdr, gamma, kind, out_tensor.data_ptr(),
             out_tensor.stride(0) * out_tensor.element_size(), out_row0, rb, re,
             scratch.data_ptr() if scratch is not None else None, nscr, lut.data_ptr(),
-            quality=_capi.QUALITY_FAST if quality == "fast" else _capi.QUALITY_BEST)
+            quality=_capi.QUALITY_FAST if quality == "fast" else _capi.QUALITY_BEST,
+            dir_map_ptr=dir_map.data_ptr() if dir_map is not None else None,
+            dir_map_pitch=dir_map.stride(0) if dir_map is not None else 0)
         _capi.check(L.pysp_develop(C.byref(a), _stream_ptr(stream)))
     return out_tensor
 
@@ -146,10 +167,10 @@ def normalize(raw, black, white, stream=None):
     require_cuda()
     L = _capi.lib()
     H, W = raw.shape
-    out = torch.empty((H, W), dtype=torch.float32, device=raw.device)
     b = (C.c_float * 4)(*[float(v) for v in black[:4]])
     w = (C.c_float * 4)(*[float(v) for v in white[:4]])
-    with torch.cuda.device(raw.device):
+    with _on(raw.device, stream):
+        out = torch.empty((H, W), dtype=torch.float32, device=raw.device)
         _capi.check(L.pysp_normalize_u16(raw.data_ptr(), raw.stride(0) * 2, out.data_ptr(), out.stride(0) * 4, H, W,
                                          b, w, _stream_ptr(stream)))
     return out
@@ -159,10 +180,10 @@ def cam_to_rgb(rgb, matrix, clip=True, gamma=False, half=False, stream=None):
     """float32 [...,3] camera RGB -> float64 3x3 -> float32 (colorize/transform.py:37-53)."""
     require_cuda()
     L = _capi.lib()
-    rgb = rgb.contiguous()
-    out = torch.empty(rgb.shape, dtype=torch.float16 if half else torch.float32, device=rgb.device)
     m = (C.c_double * 9)(*[float(v) for row in np.asarray(matrix, dtype=np.float64) for v in row])
-    with torch.cuda.device(rgb.device):
+    with _on(rgb.device, stream):
+        rgb = rgb.contiguous()
+        out = torch.empty(rgb.shape, dtype=torch.float16 if half else torch.float32, device=rgb.device)
         _capi.check(L.pysp_cam_to_lin_srgb(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, m, int(bool(clip)),
                                            int(bool(gamma)), int(bool(half)), _stream_ptr(stream)))
     return out
@@ -175,12 +196,12 @@ def wb_scale(rgb, wb, mode, normalized=False, max_wb=1.0, stream=None):
     """wb_apply / wb_undo / clip_rgb on a float32 [...,3] CUDA tensor (base_types/image_base.py:45-60, transform.py:6-19)."""
     require_cuda()
     L = _capi.lib()
-    rgb = rgb.contiguous()
     if rgb.dtype != torch.float32 or rgb.shape[-1] != 3:
         raise ValueError("wb_scale: float32 [...,3] tensor expected")
-    out = torch.empty_like(rgb)
     wb3 = (C.c_float * 3)(*[float(v) for v in (wb[:3] if wb is not None else (1.0, 1.0, 1.0))])
-    with torch.cuda.device(rgb.device):
+    with _on(rgb.device, stream):
+        rgb = rgb.contiguous()
+        out = torch.empty_like(rgb)
         _capi.check(L.pysp_wb_scale(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, wb3, float(max_wb), int(mode),
                                     int(bool(normalized)), _stream_ptr(stream)))
     return out
@@ -190,9 +211,9 @@ def rgb_to_lab_cv2(rgb, stream=None):
     """cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) on the device (the homogeneity metric's Lab; for stage tests)."""
     require_cuda()
     L = _capi.lib()
-    rgb = rgb.contiguous()
-    out = torch.empty_like(rgb)
-    with torch.cuda.device(rgb.device):
+    with _on(rgb.device, stream):
+        rgb = rgb.contiguous()
+        out = torch.empty_like(rgb)
         _capi.check(L.pysp_rgb_to_lab_cv2(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, lab_lut(rgb.device).data_ptr(),
                                           _stream_ptr(stream)))
     return out
@@ -201,9 +222,9 @@ def rgb_to_lab_cv2(rgb, stream=None):
 def srgb_gamma(rgb, stream=None):
     require_cuda()
     L = _capi.lib()
-    rgb = rgb.contiguous()
-    out = torch.empty_like(rgb)
-    with torch.cuda.device(rgb.device):
+    with _on(rgb.device, stream):
+        rgb = rgb.contiguous()
+        out = torch.empty_like(rgb)
         _capi.check(L.pysp_lin_srgb_to_srgb(rgb.data_ptr(), out.data_ptr(), rgb.numel(), _stream_ptr(stream)))
     return out
 
@@ -215,19 +236,20 @@ def fuse_exposures(brackets, ev_offsets, bias, brightest, want_count=True, strea
     n = len(brackets)
     H, W = brackets[0].shape
     dev = brackets[0].device
-    brackets = [b if b.stride(1) == 1 else b.contiguous() for b in brackets]
+    with _on(dev, stream):
+        brackets = [b if b.stride(1) == 1 else b.contiguous() for b in brackets]
     pitch = brackets[0].stride(0) * 4
     for b in brackets:
         if b.shape != (H, W) or b.dtype != torch.float32 or b.device != dev:
             raise ValueError("fuse_exposures: brackets must be float32 [H,W] on one device")
         if b.stride(0) * 4 != pitch:
             raise ValueError("fuse_exposures: brackets must share one row pitch")
-    out = torch.empty((H, W), dtype=torch.float32, device=dev)
-    cnt = torch.empty((H, W), dtype=torch.int32, device=dev) if want_count else None
     ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in brackets])
     evo = (C.c_float * n)(*[float(v) for v in ev_offsets])
     bia = (C.c_float * (3 * n))(*[float(v) for v in np.asarray(bias, dtype=np.float32).reshape(-1)])
-    with torch.cuda.device(dev):
+    with _on(dev, stream):
+        out = torch.empty((H, W), dtype=torch.float32, device=dev)
+        cnt = torch.empty((H, W), dtype=torch.int32, device=dev) if want_count else None
         _capi.check(L.pysp_fuse_exposures(ptrs, n, pitch, H, W, evo, bia, int(brightest), out.data_ptr(),
                                           out.stride(0) * 4, cnt.data_ptr() if cnt is not None else None,
                                           (cnt.stride(0) * 4) if cnt is not None else 0, _stream_ptr(stream)))
@@ -246,9 +268,9 @@ def bayer_plane_means(mosaic, stream=None):
     """np.mean of the R, G1, B, G2 planes of a float32 mosaic, bit-identical to NumPy (4 floats on the device)."""
     require_cuda()
     L = _capi.lib()
-    mosaic = _f32_2d(mosaic, "bayer_plane_means")
     H, W = mosaic.shape
-    with torch.cuda.device(mosaic.device):
+    with _on(mosaic.device, stream):
+        mosaic = _f32_2d(mosaic, "bayer_plane_means")
         nws = int(L.pysp_flat_workspace_bytes(H, W))
         ws = torch.empty(nws, dtype=torch.uint8, device=mosaic.device)
         out = torch.empty(4, dtype=torch.float32, device=mosaic.device)
@@ -261,12 +283,12 @@ def flat_frame_correction(sensor, flat, clamp_high=False, stream=None):
     """raw_correction.py:25-63 on the device; returns the corrected float32 mosaic."""
     require_cuda()
     L = _capi.lib()
-    sensor = _f32_2d(sensor, "flat_frame_correction")
-    flat = _f32_2d(flat, "flat_frame_correction")
     if flat.shape != sensor.shape or flat.device != sensor.device:
         raise ValueError("flat_frame_correction: image and flat field must have the same shape and device")
     H, W = sensor.shape
-    with torch.cuda.device(sensor.device):
+    with _on(sensor.device, stream):
+        sensor = _f32_2d(sensor, "flat_frame_correction")
+        flat = _f32_2d(flat, "flat_frame_correction")
         nws = int(L.pysp_flat_workspace_bytes(H, W))
         ws = torch.empty(nws, dtype=torch.uint8, device=sensor.device)
         out = torch.empty_like(sensor)
@@ -280,9 +302,9 @@ def find_hot_pixels_threshold(sensor, min_delta, min_neighbour_count, stream=Non
     """raw_bad_pixel_corr.py:30-65 on the device; returns a bool tensor [4, H/2, W/2] (planes R, G1, B, G2)."""
     require_cuda()
     L = _capi.lib()
-    sensor = _f32_2d(sensor, "find_hot_pixels_threshold")
     H, W = sensor.shape
-    with torch.cuda.device(sensor.device):
+    with _on(sensor.device, stream):
+        sensor = _f32_2d(sensor, "find_hot_pixels_threshold")
         masks = torch.empty((4, H // 2, W // 2), dtype=torch.uint8, device=sensor.device)
         _capi.check(L.pysp_find_hot_pixels_threshold(sensor.data_ptr(), sensor.stride(0) * 4, H, W, float(min_delta),
                                                      int(min_neighbour_count), masks.data_ptr(), _stream_ptr(stream)))
@@ -301,15 +323,15 @@ def fuse_exposures_from_debayer(images, wb, max_wb, normalized, ev_offsets, bias
                 or not t.is_contiguous() or t.device != dev:
             raise ValueError("fuse_exposures_from_debayer: contiguous float32 CUDA tensors [H,W,3] of one shape expected")
     npx = images[0].shape[0] * images[0].shape[1]
-    out = torch.empty_like(images[0])
-    cnt = torch.empty(images[0].shape, dtype=torch.int32, device=dev) if want_count else None
     ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in images])
     wb3 = (C.c_float * 3)(*[float(v) for v in wb[:3]])
     norm = (C.c_int32 * n)(*[int(bool(v)) for v in normalized])
     evo = (C.c_float * n)(*[float(v) for v in ev_offsets])
     bia = (C.c_float * n)(*[float(v) for v in bias])
     m = (C.c_double * 9)(*[float(v) for row in np.asarray(matrix, dtype=np.float64) for v in row])
-    with torch.cuda.device(dev):
+    with _on(dev, stream):
+        out = torch.empty_like(images[0])
+        cnt = torch.empty(images[0].shape, dtype=torch.int32, device=dev) if want_count else None
         _capi.check(L.pysp_fuse_exposures_from_debayer(ptrs, n, npx, wb3, float(max_wb), norm, evo, bia, int(brightest),
                                                        float(offset_max), m, out.data_ptr(),
                                                        cnt.data_ptr() if cnt is not None else None, int(bool(write_back)),

@@ -86,6 +86,20 @@ def run_reference(raw, black, white, stages, pattern="RGGB", mat=syn.MAT_XYZ_TO_
                 cnt_h=cnt_h.astype(np.uint8), cnt_v=cnt_v.astype(np.uint8), pick_h=pick_h)
 
 
+def make_nonfinite(meta):
+    """Float mosaic with +inf, -inf and NaN photosites at R, G1, G2 and B sites (debayer/ahd.py:139-145 blends the two
+    candidates multiplicatively, so a non-finite value in the candidate that is not chosen still poisons the pixel).
+    stages = 0: cv2.medianBlur's ordering of NaN is implementation-defined, so the median stages are not pinned."""
+    sensor = (syn.scene(48, 64, 9).astype(np.float32) / np.float32(16383.0)).astype(np.float32)
+    for (y, x), v in (((20, 30), np.inf), ((33, 11), np.nan), ((10, 51), -np.inf), ((41, 40), np.inf), ((8, 9), np.nan),
+                      ((0, 0), np.inf), ((47, 63), np.nan), ((24, 63), -np.inf)):
+        sensor[y, x] = v
+    with np.errstate(invalid="ignore"):
+        res = run_reference(None, None, None, 0, "RGGB", sensor_override=sensor)
+    np.savez_compressed(os.path.join(OUT, "nonfinite48x64_s0.npz"), stages=0, pattern="RGGB", **res, **meta)
+    print("nonfinite", int((~np.isfinite(res["cam"])).sum()), "non-finite values")
+
+
 def main():
     import cv2
     rh.load()
@@ -129,6 +143,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, "hdr48x64_s%d.npz" % s), stages=s, pattern="RGGB",
                             hdr=True, **res, **meta)
         print("hdr s%d" % s, res["lin"].shape)
+
+    make_nonfinite(meta)
 
     # HDR fuse (raw_hdr.py:85-158) + develop of the fused mosaic
     raw_hdr = rh.patch_hdr_ctor()

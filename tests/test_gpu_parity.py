@@ -45,6 +45,19 @@ def test_golden_hdr(eng, stages):
     assert_bit_equal(gpu_develop(eng, d["sensor"], stages, hdr=True, out="lin"), d["lin"], "HDR linear sRGB")
 
 
+def test_nonfinite_photosites(eng):
+    """+inf / -inf / NaN photosites (HDR / float mosaics): the multiplicative blend of debayer/ahd.py:139-145 poisons every
+    pixel whose other candidate is non-finite, np.clip keeps NaN; same NaN set and same finite bits as the reference."""
+    from conftest import assert_bit_equal_nan
+    d = golden("nonfinite48x64_s0")
+    dm = torch.zeros(d["sensor"].shape, dtype=torch.uint8, device="cuda")
+    t = eng.to_device(d["sensor"])
+    cam = eng.develop(t, WB, M, stages=0, out="cam", dir_map=dm)
+    assert np.array_equal(dm.cpu().numpy().astype(bool), d["pick_h"])
+    assert_bit_equal_nan(cam.cpu().numpy(), d["cam"], "camera RGB with non-finite photosites")
+    assert_bit_equal_nan(gpu_develop(eng, d["sensor"], 0), d["lin"], "linear sRGB with non-finite photosites")
+
+
 @pytest.mark.parametrize("shape,stages,seed", [((512, 768), 1, 0), ((250, 1002), 0, 1), ((1000, 1500), 3, 2),
                                                ((130, 62), 2, 3)])
 def test_against_oracle(eng, shape, stages, seed):
@@ -236,13 +249,15 @@ def test_fast_quality(eng, name):
     assert_bit_equal(img2.to_rggb().demosaic(P.QualityDemosaic.Fast).image, d["cam"], "Fast via RawRggbBayerData")
 
 
-def test_fast_quality_24mp(eng):
-    raw = syn.scene(1200, 1808, 3)
+@pytest.mark.parametrize("shape", [(1200, 1808), (3000, 4000)])
+def test_fast_quality_against_oracle(eng, shape):
+    """QualityDemosaic.Fast against the oracle on a 2 MP frame and at BASELINE config 1's size (4000x3000, 12 MP)."""
+    raw = syn.scene(shape[0], shape[1], 3)
     lin, _ = sp.develop_fast(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
     t = eng.to_device(raw)
     out = eng.develop(t, WB, M, black=syn.BLACK, white=syn.WHITE, quality="fast")
     torch.cuda.synchronize()
-    assert_bit_equal(out.cpu().numpy(), lin, "Fast 2 MP frame")
+    assert_bit_equal(out.cpu().numpy(), lin, "Fast %dx%d frame" % (shape[1], shape[0]))
 
 
 def test_large_frame_smoke(eng):

@@ -33,6 +33,21 @@ def test_hdr_branch(stages):
     assert_bit_equal(sp.to_lin_srgb(cam, m), d["lin"], "linear sRGB (HDR)")
 
 
+def test_nonfinite_photosites():
+    """+inf / -inf / NaN photosites: the reference blends the candidates multiplicatively (debayer/ahd.py:139-145), so a
+    non-finite value in either candidate poisons the pixel; cv2's Lab clamps NaN to 0.  Pinned at stages = 0 (the NaN
+    ordering of cv2.medianBlur is implementation-defined)."""
+    from conftest import assert_bit_equal_nan
+    d = golden("nonfinite48x64_s0")
+    m = sp.cam_to_lin_srgb_matrix(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    with np.errstate(invalid="ignore"):
+        cam, ex = sp.ahd_demosaic(d["sensor"], syn.wb_multipliers(), m, 0, keep=True)
+        assert np.array_equal(ex["pick_h"], d["pick_h"])
+        assert_bit_equal_nan(cam, d["cam"], "camera RGB with non-finite photosites")
+        assert_bit_equal_nan(sp.to_lin_srgb(cam, m), d["lin"], "linear sRGB with non-finite photosites")
+    assert int(np.isnan(d["cam"]).sum()) > 300
+
+
 def test_fuse_exposures():
     d = golden("fuse5_40x56")
     fused, cnt, lim, tev = sp.fuse_exposures(list(d["brackets"]), list(d["evs"]), WB)
@@ -81,6 +96,18 @@ def test_cv2_backend_is_close():
     b, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 0, backend="cv2")
     close = np.abs(a - b) <= 1e-4 * np.maximum(np.abs(a), 1e-3)
     assert close.mean() > 0.995
+
+
+def test_gate2_default_mode_reference():
+    """Parity gate (ii): the oracle (= the reference in generic mode, bit for bit) against the reference in its default
+    mode on a 1.5 MP frame: tolerance outside the neighbourhood of flips, flips equal to the reference's own noise floor."""
+    from conftest import gate2_check
+    d = golden("gate2_1024x1536_s1")
+    raw = syn.scene(int(d["H"]), int(d["W"]), int(d["seed"]))
+    lin, cam, ex = sp.develop(raw, syn.BLACK, syn.WHITE, syn.wb_multipliers(), syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ,
+                              int(d["stages"]), keep=True)
+    flips, own = gate2_check(lin, ex["pick_h"], lin, "oracle")
+    assert flips == own
 
 
 @pytest.mark.parametrize("name", ["fast_rand8x8", "fast_scene34x50", "fast_scene64x96_GBRG", "fast_flat20x28", "fast_rand66x130"])

@@ -107,6 +107,14 @@ def test_hdr_and_f32_input(emu):
         assert_bit_equal(emu_develop(emu, sensor, stages, hdr=True), sp.to_lin_srgb(cam, M), "hdr lin")
 
 
+def test_nonfinite_photosites(emu):
+    """the tile functions reproduce the reference on +inf / -inf / NaN photosites (multiplicative blend, NaN-keeping clip)"""
+    from conftest import assert_bit_equal_nan, golden
+    d = golden("nonfinite48x64_s0")
+    assert_bit_equal_nan(emu_develop(emu, d["sensor"], 0, out_kind=_capi.OUT_CAM_F32), d["cam"], "non-finite cam")
+    assert_bit_equal_nan(emu_develop(emu, d["sensor"], 0), d["lin"], "non-finite lin")
+
+
 def test_golden_through_emulation(emu):
     from conftest import golden
     d = golden("scene64x96_BGGR")
