@@ -29,7 +29,7 @@ namespace pysp {
 #define PYSP_K1_TW 60
 #endif
 #ifndef PYSP_K1_TH
-#define PYSP_K1_TH 28
+#define PYSP_K1_TH 60
 #endif
 #ifndef PYSP_K2_TW
 #define PYSP_K2_TW 60
@@ -37,7 +37,10 @@ namespace pysp {
 #ifndef PYSP_K2_TH
 #define PYSP_K2_TH 60
 #endif
-constexpr int K1_TW = PYSP_K1_TW, K1_TH = PYSP_K1_TH, K1_THREADS = 256;
+#ifndef PYSP_K1_THREADS
+#define PYSP_K1_THREADS 512
+#endif
+constexpr int K1_TW = PYSP_K1_TW, K1_TH = PYSP_K1_TH, K1_THREADS = PYSP_K1_THREADS;
 #ifndef PYSP_K2_THREADS
 #define PYSP_K2_THREADS 512
 #endif
@@ -71,12 +74,14 @@ __device__ __forceinline__ void store_tile(const float* out, const StoreParams& 
     }
 }
 
-// K1, persistent: grid = resident CTAs; each CTA walks tiles blockIdx.x, +gridDim.x, ...  The raw box of the next
+// K1, persistent: grid = resident CTAs (one 512-thread CTA per SM on 60x60 tiles: measured 4.6 % faster than two 256-thread
+// CTAs on 60x28 tiles -- the Lab region shrinks from 1.22x to 1.14x the tile, the raw box from 1.9x to 1.6x); each CTA
+// walks tiles blockIdx.x, +gridDim.x, ...  The raw box of the next
 // tile is in flight (TMA -> staging, mbarrier) while phases 1-4 of the current tile run; the finished tile leaves
 // through the staging tile by TMA store, overlapped with the next tile's phases 0-3.
 // ALGO_EAG (QualityDemosaic.Fast) runs its own phases 1-2 (eag.cuh) in the same pipeline.
 #ifndef PYSP_K1_CTAS
-#define PYSP_K1_CTAS 2
+#define PYSP_K1_CTAS 1
 #endif
 template <int ALGO>
 __global__ void __launch_bounds__(K1_THREADS, PYSP_K1_CTAS)

@@ -72,13 +72,14 @@ static void run_chain(const DevelopPlan& plan) {
 }
 
 extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
-    // tile sizes are compile-time in the kernels; the emulation instantiates the product's tiles (K1 60x28, K2 60x60) and a small
-    // one (16x8) that puts many tile seams and partial tiles into small test frames
+    // tile sizes are compile-time in the kernels; the emulation instantiates the product's tiles (K1 60x60, K2 60x60), the
+    // 60x28 K1 tile of earlier builds and small ones (16x8, 20x8) that put many tile seams and partial tiles into small frames
     DevelopPlan plan;
-    const bool product = tw == 60 && th == 28;                // the product's tiles: K1 60x28, K2 60x60
-    int rc = plan_develop(a, tw, th, tw, product ? 60 : th, &plan, g_err, sizeof(g_err));
+    const bool old = tw == 60 && th == 28;
+    int rc = plan_develop(a, tw, th, tw, old ? 60 : th, &plan, g_err, sizeof(g_err));
     if (rc) return rc;
-    if (product) run_chain<60, 28, 60, 60>(plan);
+    if (old) run_chain<60, 28, 60, 60>(plan);
+    else if (tw == 60 && th == 60) run_chain<60, 60>(plan);   // the product's tiles
     else if (tw == 56 && th == 30) run_chain<56, 30>(plan);   // a box with the fixed 8-px margin (tile width 0 mod 8)
     else if (tw == 16 && th == 8) run_chain<16, 8>(plan);
     else if (tw == 20 && th == 8) run_chain<20, 8>(plan);     // tile width 4 mod 8: box margin alternates 8 / 12 px

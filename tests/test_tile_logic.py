@@ -71,7 +71,7 @@ def emu_develop(lib, src, stages, pattern="RGGB", tile=(16, 8), black=syn.BLACK,
 def test_frames(emu, shape, stages):
     raw = syn.scene(shape[0], shape[1], 3) if shape[0] > 10 else syn.random_mosaic(shape[0], shape[1], 3)
     lin, cam = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages)
-    for tile in ((16, 8), (20, 8), (60, 28)):
+    for tile in ((16, 8), (20, 8), (60, 28), (60, 60)):
         assert_bit_equal(emu_develop(emu, raw, stages, tile=tile), lin, "lin %s" % (tile,))
         assert_bit_equal(emu_develop(emu, raw, stages, tile=tile, out_kind=_capi.OUT_CAM_F32), cam, "cam %s" % (tile,))
 
@@ -127,7 +127,7 @@ def test_fast_quality_golden(emu, name):
     """QualityDemosaic.Fast (edge-assisted Gaussian) against the reference's golden outputs."""
     from conftest import golden
     d = golden(name)
-    for tile in ((16, 8), (20, 8), (60, 28)):
+    for tile in ((16, 8), (20, 8), (60, 28), (60, 60)):
         cam = emu_develop(emu, d["raw"], 3, str(d["pattern"]), tile=tile, out_kind=_capi.OUT_CAM_F32, quality=1)
         assert_bit_equal(cam, d["cam"], "Fast camera RGB %s" % (tile,))
         assert_bit_equal(emu_develop(emu, d["raw"], 0, str(d["pattern"]), tile=tile, quality=1), d["lin"], "Fast linear sRGB")

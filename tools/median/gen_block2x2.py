@@ -1,12 +1,17 @@
 """Generator of the 2x2-block 5x5 median (cv2.medianBlur(f32, 5) semantics: exact selection).
 
-Four neighbouring outputs (y..y+1, x..x+1) share a 4x4 core of their 5x5 windows.  Per block:
-  1. sort the 16 core values (only ranks 3..12 can be the median of any of the four windows);
-  2. per output: its 9 extra values = a 4-column strip (shared by the two outputs of the same side) and a row of 5
-     (two rows of 6 values, the middle 4 sorted once per row, then one insertion per side) -> merged to a sorted 9;
-  3. 13th smallest of (core, extras) = min_i max(Z_i, E_{13-i})  (exact two-sorted-lists identity).
-Every sub-network is found by pruning a Batcher network under its precondition and checked EXHAUSTIVELY with the 0-1
-principle; the assembled program is checked on random data (ties included) against numpy.
+Four neighbouring outputs (y..y+1, x..x+1) share a 4x4 core of their 5x5 windows; the 9 other values of a window are a
+column strip of 4 (shared by the two outputs on that side), the middle 4 of a row (shared by the two outputs of that
+row) and one corner.  Per block:
+  1. sort the 16 core values; only ranks 3..12 (Z') can be the median of any of the four windows;
+  2. per side: T = sorted(Z' u strip), of which only the 6 middle ranks are needed -- shared by two outputs;
+  3. per output: the two middle ranks of T u (row middle 4) by the exact two-sorted-lists identity
+     r-th smallest of A u B = min_i max(A_i, B_{r-i}), then the corner is clamped between them:
+     13th of 25 = max(X_lo, min(corner, X_hi)).
+Every sub-network is found by pruning a sorting network under its precondition and checked EXHAUSTIVELY with the 0-1
+principle.  The assembled program is also checked exhaustively: a min/max program is monotone, so an output equals the
+median of its 25 window cells for every input iff it does for all 2^25 0/1 windows with the 11 cells outside the window
+all 0 and all 1 (`check_exhaustive`); plus random data with ties against numpy.
 Emits pysp_b200/csrc/median_block.cuh.
 """
 import itertools
@@ -171,49 +176,162 @@ class Prog:
         self.ops = keep
 
 
+def search_two_runs(n, runs, need, starts, trials, tries=8):
+    """Cheapest network (by pruning) that delivers ranks `need` of n wires holding sorted runs of the given lengths.  The
+    runs are tried on random wire subsets (run order = wire order): which wires hold which run decides what the pruning of a
+    fixed sorting network can reach.  Deterministic (seeded).  Returns (ops, network, wire groups)."""
+    rng = random.Random(0)
+    best = None
+    for t in range(trials):
+        wires = list(range(n))
+        if t:
+            rng.shuffle(wires)
+        groups, k = [], 0
+        for length in runs:
+            groups.append(sorted(wires[k:k + length]))
+            k += length
+
+        def valid(p, groups=groups):
+            return all(p[a] <= p[b] for gr in groups for a, b in zip(gr, gr[1:]))
+
+        for st in starts:
+            o, net = minimise(n, st, valid, need, need, tries=tries, seed=t)
+            if best is None or o < best[0]:
+                best = (o, net, groups)
+    return best
+
+
+# 10-input sorting network with 29 compare-exchanges
+SORT10 = [(0, 8), (1, 9), (2, 7), (3, 5), (4, 6), (0, 2), (1, 4), (5, 8), (7, 9), (0, 3), (2, 4), (5, 7), (6, 9), (0, 1), (3, 6),
+          (8, 9), (1, 5), (2, 3), (4, 8), (6, 7), (1, 2), (3, 5), (4, 6), (7, 8), (2, 3), (4, 5), (6, 7), (3, 4), (5, 6)]
+
+# 16-input sorting network with 60 compare-exchanges (10 layers)
+SORT16 = [(0, 13), (1, 12), (2, 15), (3, 14), (4, 8), (5, 6), (7, 11), (9, 10), (0, 5), (1, 7), (2, 9), (3, 4), (6, 13), (8, 14),
+          (10, 15), (11, 12), (0, 1), (2, 3), (4, 5), (6, 8), (7, 9), (10, 11), (12, 13), (14, 15), (0, 2), (1, 3), (4, 10), (5, 11),
+          (6, 7), (8, 9), (12, 14), (13, 15), (1, 2), (3, 12), (4, 6), (5, 7), (8, 10), (9, 11), (13, 14), (1, 4), (2, 6), (5, 8),
+          (7, 10), (9, 13), (11, 14), (2, 4), (3, 6), (9, 12), (11, 13), (3, 5), (6, 8), (7, 9), (10, 12), (3, 4), (5, 6), (7, 8),
+          (9, 10), (11, 12), (6, 7), (8, 9)]
+
+
+def rank_of_union(P, A, a0, B, r):
+    """r-th smallest (1-based) of A u B for sorted lists; A holds ranks a0.. (1-based) of its list, entries outside are
+    known not to matter; B is complete (1-based from 1).  min over j of max(A_{r-j}, B_j), B_0 = -inf."""
+    terms = []
+    for j in range(0, len(B) + 1):
+        i = r - j
+        if i < a0 or i >= a0 + len(A):
+            assert j > 0 or True
+            continue
+        if j == 0:
+            terms.append(A[i - a0])
+        else:
+            d = P.new()
+            P.ops.append((d, "max", A[i - a0], B[j - 1]))
+            terms.append(d)
+    return P.fold("min", terms)
+
+
 def build():
     print("minimising sub-networks ...", flush=True)
     # core: 16 arbitrary inputs, need ranks 3..12 on wires 3..12
-    core_ops, core = minimise(16, batcher(16), lambda p: True, list(range(3, 13)), list(range(3, 13)), tries=3)
+    best = None
+    for start in (SORT16, batcher(16)):
+        ops, net = minimise(16, start, lambda p: True, list(range(3, 13)), list(range(3, 13)), tries=6)
+        if best is None or ops < best[0]:
+            best = (ops, net)
+    core_ops, core = best
     print("core16 -> ranks 3..12:", len(core), "CEs,", core_ops, "ops", flush=True)
     s4_ops, s4 = minimise(4, batcher(4), lambda p: True, [0, 1, 2, 3], [0, 1, 2, 3], tries=2)
     print("sort4:", len(s4), "CEs", s4_ops, "ops")
-    # insert: wires 0..3 sorted, wire 4 free -> sorted 5
-    ins_ops, ins = minimise(5, batcher(5), lambda p: all(p[i] <= p[i + 1] for i in range(3)), list(range(5)), list(range(5)),
-                            tries=20)
-    print("insert(4+1):", len(ins), "CEs", ins_ops, "ops", ins)
-    # merge: wires 0..3 sorted (strip), wires 4..8 sorted (row) -> sorted 9
-    mrg_ops, mrg = minimise(9, batcher(9), lambda p: all(p[i] <= p[i + 1] for i in range(3)) and all(p[i] <= p[i + 1] for i in range(4, 8)),
-                            list(range(9)), list(range(9)), tries=40)
-    print("merge(4,5):", len(mrg), "CEs", mrg_ops, "ops", mrg)
+    # side merge: wires 0..3 = strip (sorted), wires 4..13 = Z' (sorted) -> ranks 4..9 (0-based) of the 14
+    mrg_ops, mrg = minimise(14, batcher(14), lambda p: all(p[i] <= p[i + 1] for i in range(3)) and all(p[i] <= p[i + 1] for i in range(4, 13)),
+                            list(range(4, 10)), list(range(4, 10)), tries=60)
+    print("merge(4,10) -> 6 middle ranks:", len(mrg), "CEs", mrg_ops, "ops", mrg)
+    # per output: the 6 known ranks of T (sorted) and the row's middle 4 (sorted) -> the two middle ranks of the 10
+    two_ops, two, two_groups = search_two_runs(10, [6, 4], [4, 5], [batcher(10), SORT10], trials=150)
+    print("middle two of (6,4):", len(two), "CEs", two_ops, "ops, runs on wires", two_groups, two)
 
     P = Prog()
     IN = [["in%d_%d" % (r, c) for c in range(6)] for r in range(6)]
     Z = P.net([IN[r][c] for r in range(1, 5) for c in range(1, 5)], core)
-    rows = {}
-    for re_ in (0, 5):
-        mid = P.net([IN[re_][c] for c in range(1, 5)], s4)
-        rows[(re_, 0)] = P.net(mid + [IN[re_][0]], ins)
-        rows[(re_, 1)] = P.net(mid + [IN[re_][5]], ins)
-    strips = {0: P.net([IN[r][0] for r in range(1, 5)], s4), 1: P.net([IN[r][5] for r in range(1, 5)], s4)}
+    Zp = Z[3:13]                                            # ranks 4..13 (1-based) of the core
+    T = {}
+    for ox, col in ((0, 0), (1, 5)):
+        strip = P.net([IN[r][col] for r in range(1, 5)], s4)
+        if mrg_ops <= 36:
+            T[ox] = P.net(strip + Zp, mrg)[4:10]            # ranks 5..10 (1-based) of Z' u strip
+        else:
+            T[ox] = [rank_of_union(P, Zp, 1, strip, r) for r in range(5, 11)]
     outs = []
     for oy in (0, 1):
+        row = 0 if oy == 0 else 5
+        mid = P.net([IN[row][c] for c in range(1, 5)], s4)
         for ox in (0, 1):
-            E = P.net(strips[ox] + rows[(0 if oy == 0 else 5, ox)], mrg)
-            # 13th smallest (1-indexed) of Z (16) u E (9): min over i=4..13 of max(Z_i, E_{13-i}), E_0 = -inf
-            terms = []
-            for i in range(4, 14):
-                j = 13 - i
-                if j == 0:
-                    terms.append(Z[i - 1])
-                else:
-                    d = P.new()
-                    P.ops.append((d, "max", Z[i - 1], E[j - 1]))
-                    terms.append(d)
-            outs.append(P.fold("min", terms))
+            corner = IN[row][0 if ox == 0 else 5]
+            # X = T u mid: 18 values once the 3 lowest / 3 highest core values are set aside; the window's median is the
+            # 10th of X u {corner} = corner clamped between X_9 and X_10
+            if two_ops <= 16:
+                w = [None] * 10
+                for k, wire in enumerate(two_groups[0]):
+                    w[wire] = T[ox][k]
+                for k, wire in enumerate(two_groups[1]):
+                    w[wire] = mid[k]
+                w = P.net(w, two)
+                lo, hi = w[4], w[5]
+            else:
+                lo = rank_of_union(P, T[ox], 5, mid, 9)
+                hi = rank_of_union(P, T[ox], 5, mid, 10)
+            m = P.new()
+            P.ops.append((m, "min", corner, hi))
+            o = P.new()
+            P.ops.append((o, "max", lo, m))
+            outs.append(o)
+    # the loop above emits outputs in (oy, ox) order, mid sorted once per row
     P.prune(outs)
     print("program: %d min/max ops for 4 outputs (%.1f per median)" % (len(P.ops), len(P.ops) / 4.0))
     return P, IN, outs
+
+
+def check_exhaustive(P, IN, outs):
+    """0-1 principle + monotonicity: every output is the median of its window for all 2^25 0/1 windows, with the 11 cells
+    of the 6x6 block outside the window all 0 and all 1."""
+    nb = 25
+    words = (1 << nb) // 64
+    base = [0xAAAAAAAAAAAAAAAA, 0xCCCCCCCCCCCCCCCC, 0xF0F0F0F0F0F0F0F0, 0xFF00FF00FF00FF00, 0xFFFF0000FFFF0000, 0xFFFFFFFF00000000]
+    idx = np.arange(words, dtype=np.uint64)
+    wires = []
+    for i in range(nb):
+        if i < 6:
+            wires.append(np.full(words, base[i], dtype=np.uint64))
+        else:
+            bit = (idx >> np.uint64(i - 6)) & np.uint64(1)
+            wires.append(np.where(bit == 1, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0)))
+    c = [np.zeros(words, dtype=np.uint64) for _ in range(5)]       # bit-sliced count of ones
+    for x in wires:
+        carry = x
+        for k in range(5):
+            t = c[k] & carry
+            c[k] = c[k] ^ carry
+            carry = t
+    expect = c[4] | (c[3] & c[2] & (c[1] | c[0]))                  # count >= 13
+    k = 0
+    for oy in (0, 1):
+        for ox in (0, 1):
+            for fill in (np.uint64(0), np.uint64(0xFFFFFFFFFFFFFFFF)):
+                env = {}
+                n = 0
+                for r in range(6):
+                    for cc in range(6):
+                        if oy <= r < oy + 5 and ox <= cc < ox + 5:
+                            env[IN[r][cc]] = wires[n]
+                            n += 1
+                        else:
+                            env[IN[r][cc]] = np.full(words, fill, dtype=np.uint64)
+                for (d, op, a, b) in P.ops:
+                    env[d] = (env[a] & env[b]) if op == "min" else (env[a] | env[b])
+                assert np.array_equal(env[outs[k]], expect), ("exhaustive check failed", oy, ox, int(fill != 0))
+            k += 1
+    print("exhaustive 0-1 check ok: 4 outputs x 2^25 windows x {outside all 0, outside all 1}")
 
 
 def check(P, IN, outs, trials=20000, seed=1):
@@ -260,6 +378,7 @@ def emit(P, IN, outs, path):
 
 if __name__ == "__main__":
     P, IN, outs = build()
+    check_exhaustive(P, IN, outs)
     check(P, IN, outs)
     here = os.path.dirname(os.path.abspath(__file__))
     emit(P, IN, outs, os.path.join(here, "..", "..", "pysp_b200", "csrc", "median_block.cuh"))
