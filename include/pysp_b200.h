@@ -43,6 +43,11 @@ extern "C" {
 #define PYSP_OUT_CAM_F32 0 /* RawDemosaicData.image: camera RGB, WB applied once (debayer/ahd.py:167) */
 #define PYSP_OUT_LIN_F32 1 /* ... .to_lin_srgb() (base_types/image_base.py:62-64) */
 #define PYSP_OUT_LIN_F16 2 /* same, stored as half */
+/* Wire-format outputs: lin_srgb_to_srgb (colorize/transform.py:89-99) applied to the linear-sRGB result and rounded to
+ * nearest into 8 / 16 bits (x * 255, x * 65535).  The reference stops at float32; these are what a caller that encodes
+ * or displays the image needs, at 3 / 6 instead of 12 bytes per pixel over PCIe. */
+#define PYSP_OUT_SRGB_U8 3
+#define PYSP_OUT_SRGB_U16 4
 
 /* const.py:3-6 (QualityDemosaic); Draft is not on the B200 path */
 #define PYSP_QUALITY_BEST 0

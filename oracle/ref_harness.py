@@ -1,9 +1,11 @@
 """Import the UNMODIFIED reference (bullbin/pySP) in THIS container, for pinning the oracle.
 
 TEST INFRASTRUCTURE ONLY -- never imported by `pysp_b200/`.  `/root/reference` does not exist on
-the GPU box, so nothing here may run in `-m gpu` tests, `smoke()` or `bench.py`; it is used by
-`tests/golden/make_golden.py` (which writes the committed fixtures) and by the optional
-`tests/test_oracle_vs_reference.py`, which skips when the reference is not mounted.
+the GPU box, so nothing here runs in `-m gpu` tests or `smoke()`; it is used by
+`tests/golden/make_golden.py` (which writes the committed fixtures), by the optional
+`tests/test_oracle_vs_reference.py`, which skips when the reference is not mounted, and by the CPU arm
+of `bench.py` (`--impl reference`, `cpu_baseline`), which imports the reference from the git-ignored
+install `baseline/_ref/pySP` (oracle/install_ref.py) when that travelled with the repo.
 
 What it does (none of it changes reference arithmetic):
   * registers the reference directory as package `pySP` (it uses absolute `pySP.*` imports,
@@ -27,8 +29,20 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PYSP_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_INSTALLED = os.path.abspath(os.path.join(_HERE, "..", "baseline", "_ref", "pySP"))     # oracle/install_ref.py
+
+
+def _reference_root():
+    env = os.environ.get("PYSP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.exists("/root/reference/debayer/ahd.py"):
+        return "/root/reference"
+    return _INSTALLED            # the copy that travels to the GPU box (bench.py's CPU arm only)
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available():
@@ -134,6 +148,24 @@ def pin_numerics(pinned=True):
         cv2.ipp.setUseIPP(not pinned)
     except Exception:
         pass
+
+
+def develop(raw_u16, black, white, stages=1, mat=None, xyz=None):
+    """The develop path exactly as a pySP user runs it (README.md:54-63): bayer_normalize -> RawBayerData.demosaic(
+    QualityDemosaic.Best, stages) -> .to_lin_srgb().  Returns float32 [H, W, 3] linear sRGB.  OpenCV mode is whatever
+    `pin_numerics` last set (default: optimised)."""
+    load()
+    from pySP.normalization import bayer_normalize
+    from pySP.image import RawBayerData
+    from pySP.base_types.image_base import BayerPattern
+    from pySP.const import QualityDemosaic
+    from pysp_b200 import synthetic as syn
+    img = RawBayerData()
+    img.sensor_scaled = bayer_normalize(raw_u16, list(black), list(white))
+    img.sensor_pattern = BayerPattern.Rggb
+    img.cam_wb = StubWhiteBalance(syn.MAT_XYZ_TO_CAM if mat is None else mat, syn.WHITE_XYZ if xyz is None else xyz)
+    img.current_ev = 10.0
+    return img.demosaic(QualityDemosaic.Best, stages).to_lin_srgb()
 
 
 def make_rggb_container(sensor_scaled, wb, ev=10.0, lim_sat=1.0, hdr=False, pattern=None):

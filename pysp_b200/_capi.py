@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PYSP_B200_LIB") or os.path.join(_HERE, "libpysp_b200.
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 CFA = {"RGGB": 1, "BGGR": 2, "GRBG": 3, "GBRG": 4}
 IN_U16, IN_F32 = 0, 1
-OUT_CAM_F32, OUT_LIN_F32, OUT_LIN_F16 = 0, 1, 2
+OUT_CAM_F32, OUT_LIN_F32, OUT_LIN_F16, OUT_SRGB_U8, OUT_SRGB_U16 = 0, 1, 2, 3, 4
 QUALITY_BEST, QUALITY_FAST = 0, 1
 MAX_BRACKETS = 16
 

@@ -121,15 +121,21 @@ PYSP_HD void store_tile_generic(const float* out, const StoreParams& st, const F
     int bx, by;
     tile_output_box<TW, TH>(st, g, x0, y0, &bx, &by);
     if (st.mode == OUT_FINAL) {
-        if (st.kind == OUT_LIN_F16) {
-#ifndef PYSP_HOST_EMU
+        if (st.kind == OUT_LIN_F16 || st.kind >= OUT_SRGB_U8) {
+            // narrow outputs: converted on the way out of the float staging tile (consecutive threads write consecutive
+            // elements of a tile row).  Quantised sRGB: round-to-nearest of the gamma-encoded value times 255 / 65535.
             PYSP_ITEMS(i, TH * TW * 3) {
                 int r = i / (TW * 3), cc = i - r * (TW * 3);
                 int gy = by + r, gx = bx + cc;
-                if (gy >= 0 && gy < st.img.rows && gx >= 0 && gx < st.img.cols)
-                    *(__half*)((char*)st.img.base + (long long)gy * st.img.pitch + (long long)gx * 2) = __float2half_rn(out[i]);
-            }
+                if (gy >= 0 && gy < st.img.rows && gx >= 0 && gx < st.img.cols) {
+                    char* dst = (char*)st.img.base + (long long)gy * st.img.pitch;
+                    if (st.kind == OUT_SRGB_U8) ((uint8_t*)dst)[gx] = (uint8_t)quantise(out[i], 255.0f);
+                    else if (st.kind == OUT_SRGB_U16) ((uint16_t*)dst)[gx] = (uint16_t)quantise(out[i], 65535.0f);
+#ifndef PYSP_HOST_EMU
+                    else ((__half*)dst)[gx] = __float2half_rn(out[i]);
 #endif
+                }
+            }
         } else {
             box_store_generic(out, st.img, bx, by, TW * 3, TH);
         }

@@ -89,7 +89,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     }
     if (a->in_kind != PYSP_IN_U16 && a->in_kind != PYSP_IN_F32)
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad in_kind %d", a->in_kind);
-    if (a->out_kind < PYSP_OUT_CAM_F32 || a->out_kind > PYSP_OUT_LIN_F16)
+    if (a->out_kind < PYSP_OUT_CAM_F32 || a->out_kind > PYSP_OUT_SRGB_U16)
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad out_kind %d", a->out_kind);
     if (!a->in || !a->out || (!a->lab_lut && a->quality == PYSP_QUALITY_BEST))
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: null buffer");
@@ -107,7 +107,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
     const int64_t esz = a->in_kind == PYSP_IN_U16 ? 2 : 4;
     if (a->in_pitch_bytes < W * esz || (a->in_pitch_bytes % esz) || ((uintptr_t)a->in % esz))
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad input pitch/alignment");
-    const int64_t osz = a->out_kind == PYSP_OUT_LIN_F16 ? 2 : 4;
+    const int64_t osz = out_kind_bytes(a->out_kind);
     if (a->out_pitch_bytes < 3 * W * osz || (a->out_pitch_bytes % osz) || ((uintptr_t)a->out % osz))
         return plan_fail(err, errn, PYSP_ERR_INVALID, "pysp_develop: bad output pitch/alignment");
     // logical (RGGB-oriented) rows of the band
@@ -141,7 +141,7 @@ static inline int plan_develop(const pysp_develop_args* a, int tw1, int th1, int
         st.img.base = (char*)a->out + (int64_t)(rb - a->out_row0) * a->out_pitch_bytes;
         st.img.pitch = a->out_pitch_bytes; st.img.rows = re - rb; st.img.cols = 3 * W; st.img.elem = (int)osz;
         st.img_row0 = rb;
-        st.tma = a->out_kind != PYSP_OUT_LIN_F16 && tma_ok(st.img, flip_x != 0, (long long)W * 12);
+        st.tma = osz == 4 && tma_ok(st.img, flip_x != 0, (long long)W * 12);
     };
     auto plane_store = [&](StoreParams& st, int buf, int row0, int rows) {
         st.mode = OUT_PLANES; st.kind = OUT_CAM_F32;

@@ -73,7 +73,8 @@ namespace pysp {
 #define PYSP_GK1 (0.45186275f)
 
 enum InKind { IN_U16 = 0, IN_F32 = 1 };
-enum OutKind { OUT_CAM_F32 = 0, OUT_LIN_F32 = 1, OUT_LIN_F16 = 2 };
+enum OutKind { OUT_CAM_F32 = 0, OUT_LIN_F32 = 1, OUT_LIN_F16 = 2, OUT_SRGB_U8 = 3, OUT_SRGB_U16 = 4 };
+static constexpr int out_kind_bytes(int kind) { return kind == OUT_SRGB_U8 ? 1 : ((kind == OUT_LIN_F16 || kind == OUT_SRGB_U16) ? 2 : 4); }
 
 struct FrameGeom {
     int H, W;            // frame size (even); flips keep the size
@@ -195,6 +196,12 @@ PYSP_HD float srgb_gamma(float v) {
     const float pw = powf(x, (float)(1.0 / 2.4));
 #endif
     return x <= 0.0031308f ? x * 12.92f : (1.055f * pw) - 0.055f;
+}
+
+// wire-format quantisation of a gamma-encoded value in [0, 1] (NaN -> 0): round half to even of v * scale
+PYSP_HD uint32_t quantise(float v, float scale) {
+    float y = fmaf(sat01(v), scale, 8388608.0f);        // v * scale <= 65535 is below 2^23: adding 2^23 rounds to an integer
+    return pysp_as_uint(y) & 0x7FFFFFu;
 }
 
 // ---- cv2 RGB->Lab (float32 path) : quantise, trilinear in the 33^3 int16 table -----------------------
@@ -344,7 +351,7 @@ PYSP_HD Rgb finish_pixel(const ColorParams& c, int out_kind, Rgb v) {
     o.r = dot3_f64(c.m_out + 0, c0, c1, c2);
     o.g = dot3_f64(c.m_out + 3, c0, c1, c2);
     o.b = dot3_f64(c.m_out + 6, c0, c1, c2);
-    if (c.gamma) { o.r = srgb_gamma(o.r); o.g = srgb_gamma(o.g); o.b = srgb_gamma(o.b); }
+    if (c.gamma || out_kind >= OUT_SRGB_U8) { o.r = srgb_gamma(o.r); o.g = srgb_gamma(o.g); o.b = srgb_gamma(o.b); }
     return o;
 }
 

@@ -77,8 +77,24 @@ def release_scratch():
         _scratch.clear()
 
 
-def to_device(a, device=None, dtype=None):
-    """NumPy / CPU tensor / CUDA tensor -> contiguous CUDA tensor (no copy if already there)."""
+def padded_pitch_elems(width, elem_size):
+    """Row length in elements whose byte pitch is a multiple of 128: TMA needs 16-byte aligned rows (6000 x 2 B is, 11548 x 2 B
+    is not), 128 keeps box rows on whole L2 lines."""
+    q = 128 // elem_size
+    return (int(width) + q - 1) // q * q
+
+
+def alloc_rows(rows, width, dtype, device):
+    """[rows, width] CUDA view over a buffer whose row pitch is padded (see padded_pitch_elems): `develop` can then move a
+    frame of ANY even width with TMA."""
+    buf = torch.empty((int(rows), padded_pitch_elems(width, torch.empty((), dtype=dtype).element_size())), dtype=dtype, device=device)
+    return buf[:, :int(width)]
+
+
+def to_device(a, device=None, dtype=None, pad_pitch=False):
+    """NumPy / CPU tensor / CUDA tensor -> CUDA tensor with unit column stride (no copy if already there).  pad_pitch: 2-D inputs
+    are uploaded into a buffer with a padded row pitch (alloc_rows), so that frames whose width is not a multiple of 16 bytes
+    still take the TMA path."""
     require_cuda()
     if isinstance(a, np.ndarray):
         if a.dtype == np.uint16:
@@ -88,12 +104,19 @@ def to_device(a, device=None, dtype=None):
         t = a
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if pad_pitch and t.dim() == 2 and (t.shape[1] * t.element_size()) % 16 != 0:
+        dst = alloc_rows(t.shape[0], t.shape[1], t.dtype, device if device is not None else (t.device if t.is_cuda else "cuda"))
+        dst.copy_(t, non_blocking=True)
+        return dst
     if not t.is_cuda:
         t = t.to(device if device is not None else "cuda", non_blocking=True)
     return t.contiguous()
 
 
-_OUT_KINDS = {"cam": _capi.OUT_CAM_F32, "lin": _capi.OUT_LIN_F32, "lin_f16": _capi.OUT_LIN_F16}
+_OUT_KINDS = {"cam": _capi.OUT_CAM_F32, "lin": _capi.OUT_LIN_F32, "lin_f16": _capi.OUT_LIN_F16,
+              "srgb_u8": _capi.OUT_SRGB_U8, "srgb_u16": _capi.OUT_SRGB_U16}
+_OUT_DTYPES = {_capi.OUT_CAM_F32: torch.float32, _capi.OUT_LIN_F32: torch.float32, _capi.OUT_LIN_F16: torch.float16,
+               _capi.OUT_SRGB_U8: torch.uint8, _capi.OUT_SRGB_U16: torch.uint16}
 
 
 def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white=None, hdr=False, gamma=False,
@@ -107,7 +130,9 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
     frame_height / in_row0   when `mosaic` holds only rows [in_row0, in_row0+rows_held) of a taller frame.
     quality     "best" = AHD (debayer_ahd), "fast" = edge-assisted Gaussian (debayer_eag; stages/hdr ignored).
     dir_map     optional CUDA uint8 tensor [>= row_end-out_row0, W]: receives the AHD direction choice (1 = horizontal).
-    Returns a CUDA tensor [row_end-row_begin, W, 3] (float32, or float16 for out="lin_f16").
+    out         "cam" (camera RGB), "lin" (linear sRGB, float32), "lin_f16", or the wire formats "srgb_u8" / "srgb_u16"
+                (lin_srgb_to_srgb, then rounded into 8 / 16 bits).
+    Returns a CUDA tensor [row_end-row_begin, W, 3] of the matching dtype.
     """
     if quality not in ("best", "fast"):
         raise NotImplementedError("Quality mode not implemented: %s" % str(quality))
@@ -131,7 +156,7 @@ def develop(mosaic, wb, cam_to_srgb, stages=1, pattern="RGGB", black=None, white
         raise ValueError("engine.develop: unsupported mosaic dtype %s" % mosaic.dtype)
     rb, re = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
     kind = _OUT_KINDS[out]
-    odt = torch.float16 if kind == _capi.OUT_LIN_F16 else torch.float32
+    odt = _OUT_DTYPES[kind]
     if out_row0 is None:
         out_row0 = rb
     dev = mosaic.device

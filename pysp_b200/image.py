@@ -149,7 +149,7 @@ class RawBayerDataFromRaw(RawBayerData):
         levels = (list(black_level_per_channel), list(white_level_per_channel))
         if keep_counts:
             self._counts_numpy = is_numpy(mosaic)
-            self._counts = as_cuda(mosaic)
+            self._counts = engine.to_device(mosaic, pad_pitch=True)
             self._levels = levels
         else:
             self.sensor_scaled = bayer_normalize(mosaic, *levels)

@@ -131,16 +131,21 @@ class SymmetricBand:
         self.rows, self.held_begin, self.held_rows = (b, e), hb, he - hb
         self.max_rows = max(r[3] - r[2] for r in self.ranges)
         device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.buf = symm.empty((self.max_rows, self.width), dtype=dtype, device=device)
-        self.handle = symm.rendezvous(self.buf, group)
+        # row pitch padded to 128 bytes: the develop kernels move 16-byte aligned rows with TMA (11548 x 2 B is not aligned)
+        from .engine import padded_pitch_elems
+        self.pitch = padded_pitch_elems(self.width, torch.empty((), dtype=dtype).element_size())
+        self.store = symm.empty((self.max_rows, self.pitch), dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.store, group)
+        self.buf = self.store[:, :self.width]
         self.peers = {}
         for peer in range(self.world):
             if peer != self.rank:
                 pb, pe, phb, phe = self.ranges[peer]
                 r0, r1 = max(pb, hb), min(pe, he)          # rows of the peer's band that I hold as halo
                 if r0 < r1:
-                    view = self.handle.get_buffer(peer, (self.max_rows, self.width), dtype, 0)
-                    self.peers[peer] = (view[r0 - phb:r1 - phb], self.buf[r0 - hb:r1 - hb])
+                    view = self.handle.get_buffer(peer, (self.max_rows, self.pitch), dtype, 0)
+                    # whole padded rows travel: one contiguous peer-to-peer copy per neighbour
+                    self.peers[peer] = (view[r0 - phb:r1 - phb], self.store[r0 - hb:r1 - hb])
 
     def band(self):
         """[band_rows, W] view of the shared buffer where this rank's own rows live."""

@@ -19,7 +19,7 @@ class FramePipeline:
         self.h, self.w = int(height), int(width)
         self.kw = dict(wb=wb, cam_to_srgb=cam_to_srgb, stages=stages, pattern=pattern, black=black, white=white,
                        hdr=hdr, gamma=gamma, out=out)
-        self.out_dtype = torch.float16 if out == "lin_f16" else torch.float32
+        self.out_dtype = engine._OUT_DTYPES[engine._OUT_KINDS[out]]
         self.depth = depth
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream() for _ in range(depth)]
@@ -36,7 +36,7 @@ class FramePipeline:
         return self.h * self.w * 2
 
     def d2h_bytes(self):
-        return self.h * self.w * 3 * (2 if self.out_dtype == torch.float16 else 4)
+        return self.h * self.w * 3 * torch.empty((), dtype=self.out_dtype).element_size()
 
     def run(self, host_frames, host_outputs):
         """host_frames[i] (int16/uint16 bits, ideally pinned) -> host_outputs[i] (pinned).  Returns after
@@ -49,6 +49,20 @@ class FramePipeline:
                 with torch.cuda.stream(s):
                     self.d_in[k].copy_(src, non_blocking=True)
                     engine.develop(self.d_in[k], out_tensor=self.d_out[k], stream=s, **self.kw)
+                    dst.copy_(self.d_out[k], non_blocking=True)
+            for s in self.streams:
+                s.synchronize()
+
+    def run_copies_only(self, host_frames, host_outputs):
+        """The copies of `run` without the kernels: the same pinned buffers, byte counts, streams and order, one
+        cudaMemcpyAsync per copy (what `Tensor.copy_(non_blocking=True)` issues between pinned host and device memory).
+        Its rate is the ceiling the host <-> device path of this box puts on `run`."""
+        assert len(host_frames) == len(host_outputs)
+        with torch.cuda.device(self.device):
+            for i, (src, dst) in enumerate(zip(host_frames, host_outputs)):
+                k = i % self.depth
+                with torch.cuda.stream(self.streams[k]):
+                    self.d_in[k].copy_(src, non_blocking=True)
                     dst.copy_(self.d_out[k], non_blocking=True)
             for s in self.streams:
                 s.synchronize()

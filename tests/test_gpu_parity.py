@@ -129,6 +129,21 @@ def test_fused_outputs(eng):
     srgb = gpu_develop(eng, raw, 1, gamma=True)
     ref = sp.lin_srgb_to_srgb(lin)
     assert np.all(np.abs(srgb - ref) <= 1e-4 * np.maximum(np.abs(ref), 1e-3))
+    # wire formats: the gamma-encoded value rounded to nearest into 8 / 16 bits; the gamma is toleranced (1e-4), so a
+    # value within that distance of a rounding boundary may land on the neighbouring code
+    for kind, scale, dt in (("srgb_u8", 255.0, np.uint8), ("srgb_u16", 65535.0, np.uint16)):
+        q = gpu_develop(eng, raw, 1, out=kind)
+        assert q.dtype == dt and q.shape == lin.shape
+        exact = ref.astype(np.float64) * scale
+        want = np.rint(exact)
+        d = np.abs(q.astype(np.float64) - want)
+        assert d.max() <= 1
+        near = np.abs(exact - np.floor(exact) - 0.5) <= 1e-4 * scale
+        assert not (d > 0)[~near].any(), "%s differs away from rounding boundaries" % kind
+    for pattern in ("BGGR", "GBRG"):           # flipped stores of the narrow kinds
+        q = gpu_develop(eng, raw, 1, pattern=pattern, out="srgb_u8")
+        f = gpu_develop(eng, raw, 1, pattern=pattern, gamma=True)
+        assert np.abs(q.astype(np.float64) - np.rint(f.astype(np.float64) * 255.0)).max() <= 1
 
 
 def test_pointwise_entry_points(eng):
