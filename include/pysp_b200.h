@@ -175,6 +175,33 @@ int pysp_fuse_exposures_from_debayer(float* const* images, int32_t n, int64_t n_
                                      int32_t brightest, double offset_max, const double m[9], float* out, int32_t* count,
                                      int32_t write_back, void* stream);
 
+/* ---- post-demosaic lens correction: DNG WarpRectilinear -------------------------------------- */
+
+/* compute_remapping_table (dng_warp_corr/dng_warp_rectilinear_coords.pyx:67-80) and, with `seed`,
+ * compute_offset_remapping_table (pyx:82-95): table[H][W][2] float32 = the source position (x', y') of every pixel under
+ * the radial (kr0..kr3) + tangential (kt0, kt1) model, k = {kr0, kr1, kr2, kr3, kt0, kt1}; cam_center_norm in [0,1];
+ * seed = prior mapping [H][W][2] or NULL for the pixel grid.  Within 2 ulp of the reference (it calls libm's powf). */
+int pysp_warp_rectilinear_table(float* table, int64_t table_pitch_bytes, int32_t height, int32_t width, const float k[6],
+                                float cam_center_norm_x, float cam_center_norm_y, float scale, const float* seed,
+                                int64_t seed_pitch_bytes, void* stream);
+
+/* cv2.remap(plane, clip(map_x, 0, W-1), clip(map_y, 0, H-1), cv2.INTER_LANCZOS4) as apply_opcode_3_warp calls it
+ * (dng_warp_corr/chan_distortion_corr.py:94-97) on one plane of an interleaved float32 image: element (y, x) of the plane
+ * is src[y * pitch/4 + x * step].  map = [H][W][2] float32 (x', y'), e.g. from pysp_warp_rectilinear_table.
+ * lanczos_tab: device copy of OpenCV's float32 [32][8] Lanczos-4 table (pysp_b200/data/lanczos4_tab_f32.npy).
+ * dst must not overlap src. */
+int pysp_remap_lanczos4(const float* src, int64_t src_pitch_bytes, int32_t src_step, float* dst, int64_t dst_pitch_bytes,
+                        int32_t dst_step, int32_t height, int32_t width, const float* map, int64_t map_pitch_bytes,
+                        const float* lanczos_tab, void* stream);
+
+/* opcode_warp_rectilinear (dng_warp_corr/chan_distortion_corr.py:53-98) for all planes of a contiguous interleaved image
+ * [H][W][planes] in one kernel: coordinates are computed in registers, no table goes through HBM.  coeffs[planes][6];
+ * prior = optional [H][W][planes][2] (stack_warp_prior, chan_distortion_corr.py:10-41).  dst must not overlap src (the
+ * reference writes each plane back in place after remapping it; the caller copies dst over src for that). */
+int pysp_warp_rectilinear_apply(const float* src, float* dst, int32_t height, int32_t width, int32_t planes, const float* coeffs,
+                                float cam_center_norm_x, float cam_center_norm_y, float scale, const float* prior,
+                                const float* lanczos_tab, void* stream);
+
 /* Bench instrumentation (no reference counterpart): when enabled, pysp_develop brackets each kernel launch
  * with CUDA events on the launching stream; collect() synchronises them and returns, per kernel slot
  * (0 = ahd_select_kernel, 1 = median_stage_kernel; 4 slots), the summed device milliseconds and launch

@@ -17,17 +17,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
 
-def build(reference_root="/root/reference", force=False):
-    pyx = os.path.join(reference_root, "debayer", "ahd_homogeneity_cython.pyx")
+def build(reference_root="/root/reference", force=False, module=("debayer", "ahd_homogeneity_cython")):
+    """`module` = (sub-package, name): the homogeneity map (default) or ("dng_warp_corr", "dng_warp_rectilinear_coords"),
+    the reference's other native component (the DNG WarpRectilinear coordinate table)."""
+    pyx = os.path.join(reference_root, module[0], module[1] + ".pyx")
     if not os.path.exists(pyx):
         return None
     import numpy
     os.makedirs(OUT, exist_ok=True)
     ext = sysconfig.get_config_var("EXT_SUFFIX")
-    so = os.path.join(OUT, "ahd_homogeneity_cython" + ext)
+    so = os.path.join(OUT, module[1] + ext)
     if os.path.exists(so) and not force and os.path.getmtime(so) >= os.path.getmtime(pyx):
         return so
-    c_file = os.path.join(OUT, "ahd_homogeneity_cython.c")
+    c_file = os.path.join(OUT, module[1] + ".c")
     subprocess.check_call([sys.executable, "-m", "cython", "-3", pyx, "-o", c_file])
     cmd = ["/usr/bin/gcc", "-shared", "-fPIC", "-O2", "-fopenmp", "-ffp-contract=off",
            "-Wno-unused-function", "-Wno-cpp",
@@ -40,3 +42,4 @@ def build(reference_root="/root/reference", force=False):
 if __name__ == "__main__":
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     print(build(root, force=True))
+    print(build(root, force=True, module=("dng_warp_corr", "dng_warp_rectilinear_coords")))

@@ -92,6 +92,15 @@ def lib():
                                                    C.POINTER(C.c_float), C.c_int32, C.c_double, C.POINTER(C.c_double),
                                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.pysp_fuse_exposures_from_debayer.restype = C.c_int
+    L.pysp_warp_rectilinear_table.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_float,
+                                              C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    L.pysp_warp_rectilinear_table.restype = C.c_int
+    L.pysp_remap_lanczos4.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.pysp_remap_lanczos4.restype = C.c_int
+    L.pysp_warp_rectilinear_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                                              C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pysp_warp_rectilinear_apply.restype = C.c_int
     L.pysp_timing_enable.argtypes = [C.c_int32]
     L.pysp_timing_enable.restype = None
     L.pysp_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]

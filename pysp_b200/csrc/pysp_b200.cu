@@ -20,6 +20,7 @@
 #include "median_stage.cuh"
 #include "pointwise.cuh"
 #include "prepost.cuh"
+#include "warp.cuh"
 #include "develop_plan.h"
 
 namespace pysp {
@@ -773,6 +774,85 @@ int pysp_fuse_exposures_from_debayer(float* const* images, int32_t n, int64_t n_
     for (int i = 0; i < 9; ++i) p.m[i] = m[i];
     fuse_cam_kernel<<<grid_for(n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("fuse_cam_kernel");
+}
+
+}  // extern "C"
+
+// ---- DNG WarpRectilinear (warp.cuh) ---------------------------------------------------------------------------------
+namespace {
+// host scalars of the entry points (dng_warp_rectilinear_coords.pyx:73-77), with the reference's C types: unsigned * float,
+// libm powf, np.sqrt of the float sum as a Python float rounded into `cdef float m`
+WarpGeom warp_geom(int H, int W, float cnx, float cny, float scale) {
+    WarpGeom g;
+    g.H = H; g.W = W; g.scale = scale;
+    const unsigned width = (unsigned)W, height = (unsigned)H;
+    g.cx = (width - 1) * cnx;
+    g.cy = (height - 1) * cny;
+    float a = fabsf((width - 1) - g.cx), b = fabsf(-g.cx);
+    const float mdx = a > b ? a : b;
+    a = fabsf((height - 1) - g.cy); b = fabsf(-g.cy);
+    const float mdy = a > b ? a : b;
+    volatile float s = powf(mdx, 2.0f) + powf(mdy, 2.0f);
+    g.m = (float)sqrt((double)s);
+    return g;
+}
+}  // namespace
+
+extern "C" {
+
+int pysp_warp_rectilinear_table(float* table, int64_t table_pitch, int32_t H, int32_t W, const float k[6], float cnx, float cny,
+                                float scale, const float* seed, int64_t seed_pitch, void* stream) {
+    if (!table || !k) return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_table: null pointer");
+    if (H < 1 || W < 1) return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_table: empty image");
+    if (table_pitch < 8LL * W || (table_pitch % 8) || ((uintptr_t)table % 8) || (seed && (seed_pitch < 8LL * W || (seed_pitch % 8) || ((uintptr_t)seed % 8))))
+        return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_table: tables are [H][W][2] float32, 8-byte aligned rows");
+    int rc = ensure_device();
+    if (rc) return rc;
+    WarpTableParams p;
+    p.g = warp_geom(H, W, cnx, cny, scale);
+    if (!(p.g.m > 0.0f)) return fail(PYSP_ERR_INVALID, "float division");      // the reference raises ZeroDivisionError (1x1 image)
+    for (int i = 0; i < 6; ++i) p.k[i] = k[i];
+    p.seed = seed; p.seed_pitch = seed_pitch; p.table = table; p.table_pitch = table_pitch;
+    warp_table_kernel<<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("warp_table_kernel");
+}
+
+int pysp_remap_lanczos4(const float* src, int64_t src_pitch, int32_t src_step, float* dst, int64_t dst_pitch, int32_t dst_step,
+                        int32_t H, int32_t W, const float* map, int64_t map_pitch, const float* lanczos_tab, void* stream) {
+    if (!src || !dst || !map || !lanczos_tab) return fail(PYSP_ERR_INVALID, "pysp_remap_lanczos4: null pointer");
+    if (H < 1 || W < 1 || src_step < 1 || dst_step < 1) return fail(PYSP_ERR_INVALID, "pysp_remap_lanczos4: bad geometry");
+    if (src == dst) return fail(PYSP_ERR_INVALID, "pysp_remap_lanczos4: in-place remapping is not possible (gather)");
+    if ((src_pitch % 4) || (dst_pitch % 4) || map_pitch < 8LL * W || (map_pitch % 8) || ((uintptr_t)map % 8))
+        return fail(PYSP_ERR_INVALID, "pysp_remap_lanczos4: bad pitch / alignment");
+    int rc = ensure_device();
+    if (rc) return rc;
+    RemapParams p;
+    p.H = H; p.W = W; p.src = src; p.src_pitch = src_pitch; p.src_step = src_step; p.dst = dst; p.dst_pitch = dst_pitch;
+    p.dst_step = dst_step; p.map = map; p.map_pitch = map_pitch; p.tab = lanczos_tab;
+    remap_lanczos4_kernel<<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("remap_lanczos4_kernel");
+}
+
+int pysp_warp_rectilinear_apply(const float* src, float* dst, int32_t H, int32_t W, int32_t planes, const float* coeffs, float cnx,
+                                float cny, float scale, const float* prior, const float* lanczos_tab, void* stream) {
+    if (!src || !dst || !coeffs || !lanczos_tab) return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_apply: null pointer");
+    if (src == dst) return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_apply: source and destination must differ (gather)");
+    if (H < 1 || W < 1 || planes < 1 || planes > PYSP_WARP_MAX_PLANES)
+        return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_apply: 1..%d planes", PYSP_WARP_MAX_PLANES);
+    if (prior && ((uintptr_t)prior % 8)) return fail(PYSP_ERR_INVALID, "pysp_warp_rectilinear_apply: prior must be 8-byte aligned");
+    int rc = ensure_device();
+    if (rc) return rc;
+    WarpApplyParams p;
+    p.g = warp_geom(H, W, cnx, cny, scale);
+    if (!(p.g.m > 0.0f)) return fail(PYSP_ERR_INVALID, "float division");
+    p.planes = planes;
+    for (int c = 0; c < planes; ++c)
+        for (int i = 0; i < 6; ++i) p.k[c][i] = coeffs[c * 6 + i];
+    p.prior = prior; p.src = src; p.dst = dst; p.tab = lanczos_tab;
+    const long long tiles = (long long)((W + 31) / 32) * ((H + 7) / 8);
+    const long long cap = 148LL * 32;
+    warp_apply_kernel<<<(int)(tiles < cap ? tiles : cap), 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("warp_apply_kernel");
 }
 
 }  // extern "C"

@@ -366,3 +366,81 @@ def fuse_exposures_from_debayer(images, wb, max_wb, normalized, ev_offsets, bias
 
 def kernel_launches():
     return int(_capi.lib().pysp_kernel_launches())
+
+
+# ---- DNG WarpRectilinear (include/pysp_b200.h: post-demosaic lens correction) ---------------------------------------
+_LANCZOS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lanczos4_tab_f32.npy")
+_lanczos_dev = {}
+
+
+def lanczos_tab(device):
+    """Device copy of OpenCV's float32 [32][8] Lanczos-4 table (see tools/harvest_lanczos4.py)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    with _lock:
+        t = _lanczos_dev.get(idx)
+        if t is None:
+            t = torch.from_numpy(np.ascontiguousarray(np.load(_LANCZOS), dtype=np.float32)).to("cuda:%d" % idx)
+            _lanczos_dev[idx] = t
+    return t
+
+
+def warp_table(height, width, coeffs, cam_center_norm, scale=1.0, seed=None, device=None, stream=None):
+    """compute_remapping_table / compute_offset_remapping_table (dng_warp_rectilinear_coords.pyx:67-95) on the device:
+    float32 CUDA tensor [H, W, 2]."""
+    require_cuda()
+    L = _capi.lib()
+    dev = seed.device if seed is not None else torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    k = (C.c_float * 6)(*[float(v) for v in coeffs])
+    with _on(dev, stream):
+        if seed is not None:
+            if not seed.is_cuda or seed.dtype != torch.float32 or tuple(seed.shape) != (height, width, 2):
+                raise ValueError("warp_table: seed must be a float32 CUDA tensor [H, W, 2]")
+            seed = seed.contiguous()
+        table = torch.empty((height, width, 2), dtype=torch.float32, device=dev)
+        _capi.check(L.pysp_warp_rectilinear_table(table.data_ptr(), width * 8, height, width, k, float(cam_center_norm[0]),
+                                                  float(cam_center_norm[1]), float(scale),
+                                                  seed.data_ptr() if seed is not None else None, width * 8, _stream_ptr(stream)))
+    return table
+
+
+def remap_lanczos4(image, plane, table, stream=None):
+    """cv2.remap(image[:, :, plane], clip(table[..., 0]), clip(table[..., 1]), INTER_LANCZOS4): float32 CUDA tensor [H, W]."""
+    require_cuda()
+    L = _capi.lib()
+    if not image.is_cuda or image.dtype != torch.float32 or image.dim() != 3 or not image.is_contiguous():
+        raise ValueError("remap_lanczos4: contiguous float32 CUDA tensor [H, W, C] expected")
+    H, W, Cn = image.shape
+    with _on(image.device, stream):
+        table = table.contiguous()
+        out = torch.empty((H, W), dtype=torch.float32, device=image.device)
+        _capi.check(L.pysp_remap_lanczos4(image.data_ptr() + 4 * int(plane), W * Cn * 4, Cn, out.data_ptr(), W * 4, 1, H, W,
+                                          table.data_ptr(), W * 8, lanczos_tab(image.device).data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def warp_rectilinear(image, coeffs, cam_center_norm, scale=1.0, prior=None, stream=None):
+    """opcode_warp_rectilinear (chan_distortion_corr.py:53-98) for all planes in one kernel.  image: contiguous float32 CUDA
+    tensor [H, W, C]; coeffs [C][6]; prior optional float32 [H, W, C, 2].  Returns a new tensor."""
+    require_cuda()
+    L = _capi.lib()
+    if not image.is_cuda or image.dtype != torch.float32 or image.dim() != 3:
+        raise ValueError("warp_rectilinear: float32 CUDA tensor [H, W, C] expected")
+    H, W, Cn = image.shape
+    flat = [float(v) for row in coeffs for v in row]
+    if len(flat) != 6 * Cn:
+        raise ValueError("warp_rectilinear: one coefficient set of 6 per plane")
+    k = (C.c_float * len(flat))(*flat)
+    with _on(image.device, stream):
+        image = image.contiguous()
+        if prior is not None:
+            if not prior.is_cuda or prior.dtype != torch.float32 or tuple(prior.shape) != (H, W, Cn, 2):
+                raise ValueError("warp_rectilinear: prior must be a float32 CUDA tensor [H, W, C, 2]")
+            prior = prior.contiguous()
+        out = torch.empty_like(image)
+        _capi.check(L.pysp_warp_rectilinear_apply(image.data_ptr(), out.data_ptr(), H, W, Cn, k, float(cam_center_norm[0]),
+                                                  float(cam_center_norm[1]), float(scale),
+                                                  prior.data_ptr() if prior is not None else None,
+                                                  lanczos_tab(image.device).data_ptr(), _stream_ptr(stream)))
+    return out
