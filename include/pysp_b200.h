@@ -9,8 +9,19 @@
  *  - plain C types only; every image pointer is a DEVICE pointer owned by the caller (e.g. a torch
  *    tensor's data_ptr()) unless the name ends in `_host`;
  *  - asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to void*; NULL = default
- *    stream) on the current device; the library allocates nothing and keeps no mutable global state
- *    (scratch is caller-provided), so calls are re-entrant across streams, devices and threads;
+ *    stream) on the current device.  The library allocates NO device memory and makes no synchronising
+ *    call: scratch and workspaces are caller-provided.  What it does keep, all host-side and mutex-guarded, so
+ *    calls are re-entrant across streams, devices and threads:
+ *      . per device, the launch set-up of the develop kernels (shared-memory opt-in, persistent grid sizes),
+ *        queried on the first pysp_develop on that device; later calls only launch kernels (capturable in a
+ *        CUDA graph);
+ *      . the verdict of the last normalisation-division check (exhaustive over the 65536 sensor codes of one
+ *        level set; re-done when the levels change);
+ *      . for pysp_bayer_plane_means / pysp_flat_frame_correction, the NumPy summation trees of the last 8
+ *        plane sizes (host memory, oldest dropped); their tables are copied into the caller's workspace with
+ *        cudaMemcpyAsync from pageable host memory on every call (so these two are not graph-capturable);
+ *      . the event pairs of the bench instrumentation while pysp_timing_enable(1) is in effect;
+ *      . the test hook PYSP_DISABLE_TMA, read once per process;
  *  - return value: PYSP_OK or a negative code; pysp_last_error() returns the calling thread's message.
  *    PYSP_ERR_INVALID maps to the reference's ValueError/AssertionError cases, PYSP_ERR_UNSUPPORTED to
  *    NotImplementedError (image.py:152,176), PYSP_ERR_CUDA to a CUDA runtime failure;
@@ -117,13 +128,17 @@ int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n_pixels, const dou
                          int32_t apply_gamma, int32_t out_f16, void* stream);
 
 /* RawDemosaicData.wb_apply / wb_undo (base_types/image_base.py:45-60) and clip_rgb (colorize/transform.py:6-19) on
- * n_pixels RGB float32.  mode 0 (PYSP_WB_APPLY): x * wb[c] in float32.  mode 1 (PYSP_WB_UNDO): float32(float64(x) / wb[c]),
- * after x * max_wb in float32 when `normalized`.  mode 2 (PYSP_CLIP01): clip to [0,1].  `out` may alias `in`. */
+ * n_pixels RGB float32.  mode 0 (PYSP_WB_APPLY): x * wb[c].  mode 1 (PYSP_WB_UNDO): float32(float64(x) / wb[c]), after
+ * x * max_wb when `normalized`.  mode 2 (PYSP_CLIP01): clip to [0,1].  `out` may alias `in`.
+ * The reference multiplies with whatever dtype its coefficient object has (NumPy promotion): wb_is_f64 = 0 means float32
+ * coefficients (products in float32, the EXIF path), 1 means float64 coefficients or a Python list (product / quotient in
+ * float64, rounded to float32 once); max_is_f64 = 1 when max(wb) is a NumPy float64 scalar (the image is then promoted
+ * to float64 before the division), 0 when it is a float32 or a Python float (product rounded to float32 first). */
 #define PYSP_WB_APPLY 0
 #define PYSP_WB_UNDO 1
 #define PYSP_CLIP01 2
-int pysp_wb_scale(const float* in, float* out, int64_t n_pixels, const float wb[3], float max_wb, int32_t mode,
-                  int32_t normalized, void* stream);
+int pysp_wb_scale(const float* in, float* out, int64_t n_pixels, const double wb[3], double max_wb, int32_t mode,
+                  int32_t normalized, int32_t wb_is_f64, int32_t max_is_f64, void* stream);
 
 /* cv2.cvtColor(float32 RGB -> Lab) as the homogeneity metric uses it (debayer/ahd.py:58,62), stand-alone for stage tests:
  * n_pixels RGB float32 -> Lab float32.  `lab_lut` is the packed device table (pysp_lab_lut_pack_host). */

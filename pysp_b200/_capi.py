@@ -65,8 +65,8 @@ def lib():
     L.pysp_cam_to_lin_srgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p]
     L.pysp_cam_to_lin_srgb.restype = C.c_int
-    L.pysp_wb_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_int32,
-                                C.c_void_p]
+    L.pysp_wb_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_void_p]
     L.pysp_wb_scale.restype = C.c_int
     L.pysp_rgb_to_lab_cv2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.pysp_rgb_to_lab_cv2.restype = C.c_int

@@ -43,7 +43,7 @@ class RawDemosaicData:
         if not self._wb_applied:
             want_np = is_numpy(self.image)
             img = as_cuda(self.image, torch.float32)
-            self.image = give_back(engine.wb_scale(img, np.asarray(self._wb_coeff, dtype=np.float32), engine.WB_APPLY), want_np)
+            self.image = give_back(engine.wb_scale(img, self._wb_coeff, engine.WB_APPLY), want_np)
             self._wb_applied = True
 
     def wb_undo(self):
@@ -51,9 +51,10 @@ class RawDemosaicData:
         if self._wb_applied:
             want_np = is_numpy(self.image)
             img = as_cuda(self.image, torch.float32)
-            wb = np.asarray(self._wb_coeff, dtype=np.float32)
-            self.image = give_back(engine.wb_scale(img, wb, engine.WB_UNDO, normalized=self._wb_normalized,
-                                                   max_wb=float(max(wb))), want_np)
+            # the coefficients keep their dtype (float32 array, float64 array or Python list): NumPy's promotion decides in
+            # the reference whether products and quotients are float32 or float64 (engine.wb_dtype_flags)
+            self.image = give_back(engine.wb_scale(img, self._wb_coeff, engine.WB_UNDO, normalized=self._wb_normalized,
+                                                   max_wb=float(max(self._wb_coeff))), want_np)
             self._wb_applied = False
             self._wb_normalized = False
 

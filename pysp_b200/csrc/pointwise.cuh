@@ -93,18 +93,22 @@ __global__ void __launch_bounds__(256) matrix_kernel(MatrixParams p) {
 }
 
 // RawDemosaicData.wb_apply / wb_undo (base_types/image_base.py:45-60) and clip_rgb (colorize/transform.py:6-19) on
-// [n][3] float32 pixels.  mode 0: x * wb[c] (float32).  mode 1: float32(float64(x [* max_wb]) / wb[c]).  mode 2: clip to [0,1].
-struct WbParams { const float* in; float* out; long long n; float wb[3]; float max_wb; int mode; int normalized; };
+// [n][3] float32 pixels.  mode 0: x * wb[c].  mode 1: float32(float64(x [* max_wb]) / wb[c]).  mode 2: clip to [0,1].
+// The coefficients keep the dtype the caller's object has, as NumPy's promotion does in the reference: float32 coefficients
+// multiply in float32; float64 ones (wb_f64) make the product a float64 that is rounded to float32 once; the normalisation
+// factor max(wb) multiplies in float32 unless it is a NumPy float64 scalar (max_f64), which promotes the image to float64.
+struct WbParams { const float* in; float* out; long long n; double wb[3]; double max_wb; int mode; int normalized; int wb_f64, max_f64; };
 __global__ void __launch_bounds__(256) wb_kernel(WbParams p) {
     const long long total = 3 * p.n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % 3);
         float v = p.in[i];
         if (p.mode == 0) {
-            v = v * p.wb[c];
+            v = p.wb_f64 ? __double2float_rn(__dmul_rn((double)v, p.wb[c])) : v * (float)p.wb[c];
         } else if (p.mode == 1) {
-            if (p.normalized) v = v * p.max_wb;
-            v = __double2float_rn(__ddiv_rn((double)v, (double)p.wb[c]));
+            double d = (double)v;
+            if (p.normalized) d = p.max_f64 ? __dmul_rn(d, p.max_wb) : (double)(v * (float)p.max_wb);
+            v = __double2float_rn(__ddiv_rn(d, p.wb[c]));
         } else {
             v = clip01(v);
         }

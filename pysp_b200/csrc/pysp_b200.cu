@@ -510,15 +510,16 @@ int pysp_cam_to_lin_srgb(const float* in, void* out, int64_t n, const double m[9
     return check_launch("matrix_kernel");
 }
 
-int pysp_wb_scale(const float* in, float* out, int64_t n, const float wb[3], float max_wb, int32_t mode, int32_t normalized,
-                  void* stream) {
+int pysp_wb_scale(const float* in, float* out, int64_t n, const double wb[3], double max_wb, int32_t mode, int32_t normalized,
+                  int32_t wb_is_f64, int32_t max_is_f64, void* stream) {
     if (!in || !out || n < 0 || mode < 0 || mode > 2 || (mode != 2 && !wb)) return fail(PYSP_ERR_INVALID, "pysp_wb_scale: bad argument");
     if (n == 0) return PYSP_OK;
     int rc = ensure_device();
     if (rc) return rc;
     WbParams p;
     p.in = in; p.out = out; p.n = n; p.max_wb = max_wb; p.mode = mode; p.normalized = normalized;
-    for (int c = 0; c < 3; ++c) p.wb[c] = wb ? wb[c] : 1.0f;
+    p.wb_f64 = wb_is_f64 ? 1 : 0; p.max_f64 = max_is_f64 ? 1 : 0;
+    for (int c = 0; c < 3; ++c) p.wb[c] = wb ? wb[c] : 1.0;
     wb_kernel<<<grid_for(3 * n, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("wb_kernel");
 }
@@ -571,9 +572,7 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
 namespace {
 struct PlaneSumPlan {            // host layout of NumPy's pairwise-sum tree for n elements
     std::vector<int> leaf_off, leaf_len, node_l, node_r, group_start;
-    // device copies of the five tables, one allocation per device (internal, cached; never freed before exit)
-    mutable std::mutex dev_mu;
-    mutable std::map<int, int*> dev_tables;
+    std::vector<int> packed;     // the five tables back to back, as they are uploaded into the caller's workspace
 };
 
 int build_sum_tree(long long off, long long n, PlaneSumPlan& pl, std::vector<int>& height, std::vector<int>& h_of_val) {
@@ -593,11 +592,12 @@ int build_sum_tree(long long off, long long n, PlaneSumPlan& pl, std::vector<int
 }
 
 std::shared_ptr<const PlaneSumPlan> plane_sum_plan(long long n) {
+    // host-side cache of the last few plane sizes (bounded: the oldest entry is dropped); plans are immutable and shared
     static std::mutex mu;
-    static std::map<long long, std::shared_ptr<const PlaneSumPlan>> cache;
+    static std::vector<std::pair<long long, std::shared_ptr<const PlaneSumPlan>>> cache;
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find(n);
-    if (it != cache.end()) return it->second;
+    for (auto& e : cache)
+        if (e.first == n) return e.second;
     auto pl = std::make_shared<PlaneSumPlan>();
     std::vector<int> height, unused;
     build_sum_tree(0, n, *pl, height, unused);
@@ -613,18 +613,26 @@ std::shared_ptr<const PlaneSumPlan> plane_sum_plan(long long n) {
     pl->group_start.push_back(0);
     for (int k = 1; k <= nn; ++k)
         if (k == nn || height[order[k]] != height[order[k - 1]]) pl->group_start.push_back(k);
-    cache[n] = pl;
+    pl->packed.reserve(2 * (size_t)nl + 2 * (size_t)nn + pl->group_start.size());
+    pl->packed.insert(pl->packed.end(), pl->leaf_off.begin(), pl->leaf_off.end());
+    pl->packed.insert(pl->packed.end(), pl->leaf_len.begin(), pl->leaf_len.end());
+    pl->packed.insert(pl->packed.end(), pl->node_l.begin(), pl->node_l.end());
+    pl->packed.insert(pl->packed.end(), pl->node_r.begin(), pl->node_r.end());
+    pl->packed.insert(pl->packed.end(), pl->group_start.begin(), pl->group_start.end());
+    if (cache.size() >= 8) cache.erase(cache.begin());
+    cache.emplace_back(n, pl);
     return pl;
 }
 
 long long align16(long long v) { return (v + 15) / 16 * 16; }
 
-struct FlatWorkspace { long long off_val, off_mean, off_stat, total; };
+struct FlatWorkspace { long long off_tab, off_val, off_mean, off_stat, total; };
 
 FlatWorkspace flat_workspace_layout(const PlaneSumPlan& pl) {
     FlatWorkspace w;
     long long o = 0;
     const long long nl = (long long)pl.leaf_off.size(), nn = (long long)pl.node_l.size();
+    w.off_tab = o; o = align16(o + 4 * (long long)pl.packed.size());
     w.off_val = o; o = align16(o + 4 * 4 * (nl + nn));
     w.off_mean = o; o = align16(o + 16);
     w.off_stat = o; o = align16(o + 32);
@@ -632,32 +640,16 @@ FlatWorkspace flat_workspace_layout(const PlaneSumPlan& pl) {
     return w;
 }
 
-// device copy of the tree tables (cached per device), then the two summation kernels; mean[4] lands at ws + off_mean
+// the tree tables are uploaded into the caller's workspace on the caller's stream (the library allocates nothing), then the
+// two summation kernels; mean[4] lands at ws + off_mean.  The host tables are pageable memory: cudaMemcpyAsync stages
+// them before it returns, so the plan may be evicted from the host cache afterwards.
 int launch_plane_means(const float* mosaic, long long pitch, int H, int W, char* ws, const PlaneSumPlan& pl, const FlatWorkspace& lay,
                        PlaneSumTables* tables, cudaStream_t stream) {
     const int nl = (int)pl.leaf_off.size(), nn = (int)pl.node_l.size(), ng = (int)pl.group_start.size() - 1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int* d = nullptr;
+    int* d = (int*)(ws + lay.off_tab);
     {
-        std::lock_guard<std::mutex> lk(pl.dev_mu);
-        auto it = pl.dev_tables.find(dev);
-        if (it != pl.dev_tables.end()) {
-            d = it->second;
-        } else {
-            const size_t ints = 2 * (size_t)nl + 2 * (size_t)nn + (size_t)ng + 1;
-            std::vector<int> host;
-            host.reserve(ints);
-            host.insert(host.end(), pl.leaf_off.begin(), pl.leaf_off.end());
-            host.insert(host.end(), pl.leaf_len.begin(), pl.leaf_len.end());
-            host.insert(host.end(), pl.node_l.begin(), pl.node_l.end());
-            host.insert(host.end(), pl.node_r.begin(), pl.node_r.end());
-            host.insert(host.end(), pl.group_start.begin(), pl.group_start.end());
-            cudaError_t e = cudaMalloc((void**)&d, ints * 4);
-            if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), ints * 4, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "plane means: table upload: %s", cudaGetErrorString(e));
-            pl.dev_tables[dev] = d;
-        }
+        cudaError_t e = cudaMemcpyAsync(d, pl.packed.data(), pl.packed.size() * 4, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "plane means: table upload: %s", cudaGetErrorString(e));
     }
     PlaneSumTables t;
     t.leaf_off = d; t.leaf_len = d + nl; t.node_l = d + 2 * nl; t.node_r = d + 2 * nl + nn; t.group_start = d + 2 * nl + 2 * nn;

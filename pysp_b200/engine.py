@@ -217,18 +217,34 @@ def cam_to_rgb(rgb, matrix, clip=True, gamma=False, half=False, stream=None):
 WB_APPLY, WB_UNDO, CLIP01 = 0, 1, 2
 
 
+def wb_dtype_flags(wb):
+    """(wb_is_f64, max_is_f64) for a white-balance coefficient object, by NumPy's promotion rules (NEP 50) as they act in
+    base_types/image_base.py:45-60: a float32 ndarray keeps everything in float32; a float64 ndarray promotes products and
+    `max(wb)` (a NumPy float64 scalar) to float64; a Python list / tuple becomes a float64 array in products while its
+    `max()` is a Python float (weak: the image stays float32)."""
+    if isinstance(wb, np.ndarray):
+        f64 = wb.dtype != np.float32
+        return f64, f64
+    if isinstance(wb, torch.Tensor):
+        f64 = wb.dtype != torch.float32
+        return f64, f64
+    return True, False
+
+
 def wb_scale(rgb, wb, mode, normalized=False, max_wb=1.0, stream=None):
-    """wb_apply / wb_undo / clip_rgb on a float32 [...,3] CUDA tensor (base_types/image_base.py:45-60, transform.py:6-19)."""
+    """wb_apply / wb_undo / clip_rgb on a float32 [...,3] CUDA tensor (base_types/image_base.py:45-60, transform.py:6-19).
+    `wb` keeps its dtype: see wb_dtype_flags."""
     require_cuda()
     L = _capi.lib()
     if rgb.dtype != torch.float32 or rgb.shape[-1] != 3:
         raise ValueError("wb_scale: float32 [...,3] tensor expected")
-    wb3 = (C.c_float * 3)(*[float(v) for v in (wb[:3] if wb is not None else (1.0, 1.0, 1.0))])
+    wb3 = (C.c_double * 3)(*[float(v) for v in (wb[:3] if wb is not None else (1.0, 1.0, 1.0))])
+    wb_f64, max_f64 = wb_dtype_flags(wb) if wb is not None else (False, False)
     with _on(rgb.device, stream):
         rgb = rgb.contiguous()
         out = torch.empty_like(rgb)
         _capi.check(L.pysp_wb_scale(rgb.data_ptr(), out.data_ptr(), rgb.numel() // 3, wb3, float(max_wb), int(mode),
-                                    int(bool(normalized)), _stream_ptr(stream)))
+                                    int(bool(normalized)), int(wb_f64), int(max_f64), _stream_ptr(stream)))
     return out
 
 

@@ -72,6 +72,10 @@ def fuse_exposures_from_debayer(in_exposures, target_ev=None):
     brightest = max(i for i, o in enumerate(offsets) if o == off_max)
     bias = [np.float32(1.6 ** (-0.1 * o)) for o in offsets]
     want_np = is_numpy(in_exposures[0].image)
+    if any(engine.wb_dtype_flags(e._wb_coeff)[0] for e in valid):
+        # with float64 coefficients NumPy runs the reference's wb_undo / wb_apply round trip in float64; the fused kernel
+        # implements the float32-coefficient case (the EXIF path, helpers_exif.py:79)
+        raise ValueError("fuse_exposures_from_debayer: float32 white-balance coefficients expected")
     wb = np.asarray(valid[0]._wb_coeff, dtype=np.float32)
     for e in valid:
         if not np.array_equal(np.asarray(e._wb_coeff, dtype=np.float32), wb):

@@ -196,6 +196,16 @@ def test_drop_in_containers(eng):
     norm.wb_undo()
     assert_bit_equal(norm.image, (((d["cam"] / max(wbc)).astype(np.float32) * max(wbc)).astype(np.float64) / wbc[:3]).astype(np.float32),
                      "wb_undo of a normalised image")
+    # coefficients that are not float32 (a float64 array from a solver, a Python list): the reference's NumPy expressions
+    # then run in float64 (image_base.py:45-60 under NEP 50 promotion); same bits here
+    for coeff in (wbc.astype(np.float64) * 1.00000013, [float(v) * 0.99999987 for v in wbc]):
+        obj = P.RawDemosaicData(np.array(d["cam"], copy=True), coeff, wb_norm=True)
+        obj.wb_undo()
+        ref = d["cam"] * max(coeff)
+        ref = (ref.astype(np.float64) / coeff[:3]).astype(np.float32)
+        assert_bit_equal(obj.image, ref, "wb_undo with %s coefficients" % type(coeff).__name__)
+        obj.wb_apply()
+        assert_bit_equal(obj.image, (ref * coeff[:3]).astype(np.float32), "wb_apply with %s coefficients" % type(coeff).__name__)
     # CUDA tensors in -> CUDA tensors out
     img3 = P.RawRgbgDataFromRaw.from_mosaic(torch.from_numpy(d["raw"].view(np.int16)).cuda(), list(d["black"]),
                                             list(d["white"]), "Grbg", wb, ev=10.0)

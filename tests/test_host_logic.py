@@ -99,3 +99,31 @@ def test_band_planning(height, world):
     assert prev == height
     assert parallel.frames_for_rank(10, 1, 4) == [1, 5, 9]
     assert sorted(sum([parallel.frames_for_rank(256, r, 8) for r in range(8)], [])) == list(range(256))
+
+
+def test_pySP_alias_package():
+    """`pysp_b200.compat.install_as_pySP()` makes the reference's absolute imports resolve against this package
+    (README.md:32, base_types/image_base.py:7-10) -- the same module objects, opt-in, never shadowing a real pySP."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import pysp_b200.compat as c\n"
+        "c.install_as_pySP()\n"
+        "from pySP.colorize.transform import cam_to_lin_srgb, lin_srgb_to_srgb\n"
+        "from pySP.base_types.image_base import RawDemosaicData, BayerPattern\n"
+        "from pySP.image import RawBayerDataFromRaw, RawRggbBayerData\n"
+        "from pySP.const import QualityDemosaic\n"
+        "from pySP.debayer import debayer_ahd, debayer_eag\n"
+        "from pySP.normalization import bayer_normalize\n"
+        "from pySP.raw_hdr import fuse_exposures_to_raw\n"
+        "from pySP.dng_warp_corr.chan_distortion_corr import apply_opcode_3_warp\n"
+        "import pySP, pysp_b200, pysp_b200.colorize.transform as t\n"
+        "assert cam_to_lin_srgb is t.cam_to_lin_srgb and sys.modules['pySP.colorize.transform'] is t\n"
+        "assert pySP is pysp_b200\n"
+        "c.uninstall()\n"
+        "assert 'pySP' not in sys.modules\n"
+        "print('ok')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

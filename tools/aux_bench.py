@@ -71,4 +71,15 @@ br = [engine.to_device(rng.random((H, W), dtype=np.float32)) for _ in range(5)]
 bias = np.ones((5, 3), np.float32)
 report("fuse_exposures_to_raw_n5", timed(lambda: engine.fuse_exposures(br, [0.25, 0.5, 1, 2, 4], bias, 4)), (4 * 5 + 8) * H * W,
        "5 x 4 read + 4 (mosaic) + 4 (count) written per px")
+# DNG WarpRectilinear (post-demosaic lens correction): fused all-planes kernel, and the reference's two-step form
+coeffs = [(1.0012, -0.0321, 0.0104, -0.0023, 0.0007, -0.0004), (0.9991, -0.0298, 0.0088, -0.0017, 0.0005, -0.0006),
+          (1.0005, -0.0342, 0.0121, -0.0031, 0.0009, -0.0002)]
+report("warp_rectilinear_fused_3planes", timed(lambda: engine.warp_rectilinear(rgb, coeffs, (0.4987, 0.5021))), 24 * H * W,
+       "12 read + 12 written per px (3 planes); 192 gathered taps per px come out of L1/L2")
+report("warp_table", timed(lambda: engine.warp_table(H, W, coeffs[0], (0.4987, 0.5021))), 8 * H * W, "8 written per px")
+tab0 = engine.warp_table(H, W, coeffs[0], (0.4987, 0.5021))
+report("remap_lanczos4_one_plane", timed(lambda: engine.remap_lanczos4(rgb, 0, tab0)), 16 * H * W, "8 (table) + 4 read + 4 written per px")
+out8 = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+report("develop_srgb_u8_chain", timed(lambda: engine.develop(raw, wb, m, stages=1, black=syn.BLACK, white=syn.WHITE, out="srgb_u8", out_tensor=out8)),
+       5 * H * W, "2 read + 3 written per px (whole K1 + K2 chain, 8-bit sRGB out)")
 print(json.dumps({"frame": [H, W], "peak_source": "MEASURED_PEAKS.json" if os.path.exists(pk) else "fallback", "kernels": res}))
