@@ -548,21 +548,21 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
                     if (dir == 0) {     // horizontal map: eps from the left/right neighbours (pyx:47-51)
                         const float epsl = fmaxf(fabsf(hl[a][b - 1]), fabsf(hl[a][b])), nepsl = -epsl;
                         const float epsc = fmaxf(h2[a][b - 1], h2[a][b]);
-                        n -= pass_ge(gl[a - 1][b - 1], nepsl, g2[a - 1][b - 1], epsc);
-                        n -= pass_ge(vl[a - 1][b], nepsl, v2[a - 1][b], epsc);
-                        n -= pass_ge(al[a - 1][b], nepsl, a2[a - 1][b], epsc);
-                        n -= pass_le(al[a][b - 1], epsl, a2[a][b - 1], epsc);
-                        n -= pass_le(vl[a][b], epsl, v2[a][b], epsc);
-                        n -= pass_le(gl[a][b], epsl, g2[a][b], epsc);
+                        n = count_ge(n, gl[a - 1][b - 1], nepsl, g2[a - 1][b - 1], epsc);
+                        n = count_ge(n, vl[a - 1][b], nepsl, v2[a - 1][b], epsc);
+                        n = count_ge(n, al[a - 1][b], nepsl, a2[a - 1][b], epsc);
+                        n = count_le(n, al[a][b - 1], epsl, a2[a][b - 1], epsc);
+                        n = count_le(n, vl[a][b], epsl, v2[a][b], epsc);
+                        n = count_le(n, gl[a][b], epsl, g2[a][b], epsc);
                     } else {            // vertical map: eps from the upper/lower neighbours (pyx:42-46)
                         const float epsl = fmaxf(fabsf(vl[a - 1][b]), fabsf(vl[a][b])), nepsl = -epsl;
                         const float epsc = fmaxf(v2[a - 1][b], v2[a][b]);
-                        n -= pass_ge(gl[a - 1][b - 1], nepsl, g2[a - 1][b - 1], epsc);
-                        n -= pass_ge(hl[a][b - 1], nepsl, h2[a][b - 1], epsc);
-                        n -= pass_le(al[a][b - 1], epsl, a2[a][b - 1], epsc);
-                        n -= pass_ge(al[a - 1][b], nepsl, a2[a - 1][b], epsc);
-                        n -= pass_le(hl[a][b], epsl, h2[a][b], epsc);
-                        n -= pass_le(gl[a][b], epsl, g2[a][b], epsc);
+                        n = count_ge(n, gl[a - 1][b - 1], nepsl, g2[a - 1][b - 1], epsc);
+                        n = count_ge(n, hl[a][b - 1], nepsl, h2[a][b - 1], epsc);
+                        n = count_le(n, al[a][b - 1], epsl, a2[a][b - 1], epsc);
+                        n = count_ge(n, al[a - 1][b], nepsl, a2[a - 1][b], epsc);
+                        n = count_le(n, hl[a][b], epsl, h2[a][b], epsc);
+                        n = count_le(n, gl[a][b], epsl, g2[a][b], epsc);
                     }
                     res[k] |= n << (8 * dir);
                 }

@@ -256,13 +256,15 @@ PYSP_HD LabKey lab_key(const uint4* __restrict__ lut, float r, float g, float b)
 PYSP_HD LabQ lab_interp(const LabKey& k, const uint4& e00, const uint4& e01, const uint4& e10, const uint4& e11) {
     const uint32_t sr = k.sr, sg = k.sg, sb = k.sb;
     const uint32_t wb = (16u - sb) | (sb << 8), wg0 = 16u - sg, wr0 = 16u - sr;
+    // the four (red, green) corner weights are shared by the three channels: 4 + 3 x 4 multiplies instead of 3 x 6.
+    // Integer arithmetic: any association of the weighted corner sum is exact (at most 16384 * 4096 < 2^32).
+    const uint32_t w00 = wr0 * wg0, w01 = wr0 * sg, w10 = sr * wg0, w11 = sr * sg;
     uint32_t v[3];
 #define PYSP_CH(c, f)                                                                              \
     {                                                                                              \
         uint32_t p00 = dot2_u16_u8(e00.f, wb, 0u), p01 = dot2_u16_u8(e01.f, wb, 0u);               \
         uint32_t p10 = dot2_u16_u8(e10.f, wb, 0u), p11 = dot2_u16_u8(e11.f, wb, 0u);               \
-        uint32_t q0 = p00 * wg0 + p01 * sg, q1 = p10 * wg0 + p11 * sg;                             \
-        v[c] = (q0 * wr0 + q1 * sr + 2048u) >> 12;                                                 \
+        v[c] = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 2048u) >> 12;                      \
     }
     PYSP_CH(0, x) PYSP_CH(1, y) PYSP_CH(2, z)
 #undef PYSP_CH
@@ -296,6 +298,23 @@ struct __attribute__((aligned(8))) U2 { uint32_t x, y; };
 
 // homogeneity test of one window cell (ahd_homogeneity_cython.pyx:56-58): all ones when both the lightness and the
 // chroma test pass.  pass_ge takes the lightness difference seen from the other end of the pair (-dl <= eps).
+// n + 1 if the window cell passes both tests (ahd_homogeneity_cython.pyx:56-58), else n: two compares and one predicated add
+PYSP_HD uint32_t count_le(uint32_t n, float dl, float epsl, float d2, float epsc) {
+#ifdef __CUDA_ARCH__
+    asm("{ .reg .pred p, q; setp.le.f32 p, %1, %2; setp.le.and.f32 q, %3, %4, p; @q add.u32 %0, %0, 1; }" : "+r"(n) : "f"(dl), "f"(epsl), "f"(d2), "f"(epsc));
+    return n;
+#else
+    return n + ((dl <= epsl && d2 <= epsc) ? 1u : 0u);
+#endif
+}
+PYSP_HD uint32_t count_ge(uint32_t n, float dl, float neg_epsl, float d2, float epsc) {
+#ifdef __CUDA_ARCH__
+    asm("{ .reg .pred p, q; setp.ge.f32 p, %1, %2; setp.le.and.f32 q, %3, %4, p; @q add.u32 %0, %0, 1; }" : "+r"(n) : "f"(dl), "f"(neg_epsl), "f"(d2), "f"(epsc));
+    return n;
+#else
+    return n + ((dl >= neg_epsl && d2 <= epsc) ? 1u : 0u);
+#endif
+}
 PYSP_HD uint32_t pass_le(float dl, float epsl, float d2, float epsc) {
 #ifdef __CUDA_ARCH__
     uint32_t m;

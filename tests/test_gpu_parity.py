@@ -214,6 +214,36 @@ def test_drop_in_containers(eng):
     assert_bit_equal(out.cpu().numpy(), d["lin"], "device-resident develop")
 
 
+def test_side_stream_is_safe(eng):
+    """Entry points called with a stream that is NOT torch's current stream: their temporaries and outputs are allocated on
+    that stream (engine._on), so the caching allocator cannot hand a block that queued kernels still use to tensors of the
+    current stream.  Provoked here by churning allocations of the same sizes on the current stream while the side stream
+    works; every result must equal the one computed on the current stream."""
+    raw = syn.scene(1200, 1800, 13)
+    t = eng.to_device(raw)
+    kw = dict(stages=2, black=syn.BLACK, white=syn.WHITE)
+    want = eng.develop(t, WB, M, **kw)
+    flat = torch.rand((1200, 1800), device="cuda") + 0.5
+    sens = torch.rand((1200, 1800), device="cuda")
+    want_ff = eng.flat_frame_correction(sens, flat)
+    torch.cuda.synchronize()
+    eng.release_scratch()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    outs, junk = [], []
+    for i in range(12):
+        outs.append((eng.develop(t, WB, M, stream=side, **kw), eng.flat_frame_correction(sens, flat, stream=side)))
+        for _ in range(4):                       # same-sized blocks requested on the current stream while `side` is busy
+            junk.append(torch.full((1200, 1800, 3), float(i), device="cuda"))
+            junk.append(torch.full((1200, 1800), float(i), device="cuda"))
+        junk = junk[-6:]
+    side.synchronize()
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a.view(torch.int32), want.view(torch.int32))
+        assert torch.equal(b.view(torch.int32), want_ff.view(torch.int32))
+
+
 def test_hdr_fuse(eng):
     import pysp_b200 as P
     from pysp_b200.wb_cct import CameraWhiteBalance
