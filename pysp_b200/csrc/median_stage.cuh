@@ -13,6 +13,7 @@
 #include "ahd_select.cuh"   // stage_pixel / store_tile_generic / tile_output_box
 #include "tma.cuh"
 #include "median_block.cuh"
+#include "median_block2x4.cuh"
 
 namespace pysp {
 
@@ -104,6 +105,131 @@ PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int t
             *(F2*)(ER + o) = er; *(F2*)(EB + o) = eb;
             const int ty = ly + dy - 2, tx = lx - 2;         // even tx: the pair is inside the tile or outside as a whole
             if (ty >= 0 && ty < TH && tx >= 0 && tx < TW) { *(F2*)(RP + ty * TW + tx) = r1; *(F2*)(BP + ty * TW + tx) = b1; }
+        }
+    }
+}
+
+// ---- 2x4-block variants (median_block2x4.cuh: 60.75 min/max per median).  A work item is a 2x4 block of pixels inside its 6x8
+// window; rows are 16-byte aligned (block origin and plane widths are multiples of 4), so a window row is two LDS.128.
+struct __attribute__((aligned(16))) F4 { float x, y, z, w; };
+
+template <int TW, int TH, bool EDGE>
+PYSP_D void median_phase_b4(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
+    typedef MedianTile<TW, TH> L;
+    static_assert(L::BW % 4 == 0 && L::AW % 4 == 0, "2x4 blocks need plane widths that are multiples of 4");
+    const int H = p.g.H, W = p.g.W;
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
+    const float* DR = (const float*)(smem + L::OFF_IN);
+    const float* DB = (const float*)(smem + L::OFF_IN + L::PLANE_BYTES);
+    const float* G = (const float*)(smem + L::OFF_IN + 2 * L::PLANE_BYTES);
+    float* ER = (float*)(smem + L::OFF_ER); float* EB = (float*)(smem + L::OFF_EB);
+    float* RP = (float*)(smem + L::OFF_RP); float* BP = (float*)(smem + L::OFF_BP);
+    constexpr int NBX = L::BW / 4, NBY = L::BH / 2;
+    PYSP_ITEMS(it, NBX * NBY) {
+        int by = it / NBX, bx = it - by * NBX;
+        int ly = 2 * by, lx = 4 * bx;                       // region-B coords of the block's top-left pixel
+        int y = y0 - 2 + ly, x = x0 - 2 + lx;
+        if (EDGE) { if (y < 0 || y >= H || x + 3 < 0 || x >= W) continue; }     // the whole block outside the frame
+        float w[6][8], mr[8], mb[8];
+        const int c = ly * L::AW + lx;                      // input-plane index of window cell (0,0) = pixel (y-2, x-2)
+#pragma unroll
+        for (int u = 0; u < 6; ++u)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const F4 t = ((const F4*)(DR + c + u * L::AW))[v];
+                w[u][4 * v] = t.x; w[u][4 * v + 1] = t.y; w[u][4 * v + 2] = t.z; w[u][4 * v + 3] = t.w;
+            }
+        median25_block2x4(w, mr);
+#pragma unroll
+        for (int u = 0; u < 6; ++u)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const F4 t = ((const F4*)(DB + c + u * L::AW))[v];
+                w[u][4 * v] = t.x; w[u][4 * v + 1] = t.y; w[u][4 * v + 2] = t.z; w[u][4 * v + 3] = t.w;
+            }
+        median25_block2x4(w, mb);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const float* gp = G + c + (2 + dy) * L::AW + 2;           // 8-byte aligned (c is a multiple of 4)
+            const F2 ga = ((const F2*)gp)[0], gb = ((const F2*)gp)[1];
+            const float g4[4] = {ga.x, ga.y, gb.x, gb.y};
+            F4 r1, b1, er, eb;
+            float* r1p = &r1.x; float* b1p = &b1.x; float* erp = &er.x; float* ebp = &eb.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                r1p[k] = mr[4 * dy + k] + g4[k]; b1p[k] = mb[4 * dy + k] + g4[k];
+                erp[k] = g4[k] - r1p[k]; ebp[k] = g4[k] - b1p[k];
+            }
+            const int o = (ly + dy) * L::BW + lx;
+            *(F4*)(ER + o) = er; *(F4*)(EB + o) = eb;
+            const int ty = ly + dy - 2, tx = lx - 2;         // tile coords of the block's first pixel: tx = 2 mod 4
+            if (ty >= 0 && ty < TH) {
+                if (tx >= 0 && tx + 1 < TW) { F2 t; t.x = r1.x; t.y = r1.y; *(F2*)(RP + ty * TW + tx) = t; t.x = b1.x; t.y = b1.y; *(F2*)(BP + ty * TW + tx) = t; }
+                if (tx + 2 >= 0 && tx + 3 < TW) { F2 t; t.x = r1.z; t.y = r1.w; *(F2*)(RP + ty * TW + tx + 2) = t; t.x = b1.z; t.y = b1.w; *(F2*)(BP + ty * TW + tx + 2) = t; }
+            }
+        }
+    }
+}
+
+template <int TW, int TH, bool EDGE>
+PYSP_D void median_phase_c4(const MedianParams& p, char* __restrict__ smem, int tile_x, int tile_y) {
+    typedef MedianTile<TW, TH> L;
+    static_assert(TW % 4 == 0, "2x4 blocks");
+    const int H = p.g.H, W = p.g.W;
+    const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
+    const float* ER = (const float*)(smem + L::OFF_ER); const float* EB = (const float*)(smem + L::OFF_EB);
+    const float* RP = (const float*)(smem + L::OFF_RP); const float* BP = (const float*)(smem + L::OFF_BP);
+    float* out = (float*)(smem + L::OFF_OUT);
+    constexpr int NBX = TW / 4, NBY = TH / 2;
+    PYSP_ITEMS(it, NBX * NBY) {
+        int by = it / NBX, bx = it - by * NBX;
+        int ty = 2 * by, tx = 4 * bx;
+        int y = y0 + ty, x = x0 + tx;
+        if (EDGE) { if (y >= H || x >= W) continue; }
+        int ry[6], rx[8];                                   // region-B rows/cols of the 6x8 window (REPLICATE at the frame border)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ry[k] = EDGE ? clampi(y + k - 2, H) - (y0 - 2) : ty + k;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rx[k] = EDGE ? clampi(x + k - 2, W) - (x0 - 2) : tx + k;
+        float w[6][8], mr[8], mb[8];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            if (EDGE) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) w[u][v] = ER[ry[u] * L::BW + rx[v]];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const F4 t = ((const F4*)(ER + ry[u] * L::BW + tx))[v];
+                    w[u][4 * v] = t.x; w[u][4 * v + 1] = t.y; w[u][4 * v + 2] = t.z; w[u][4 * v + 3] = t.w;
+                }
+            }
+        }
+        median25_block2x4(w, mr);
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            if (EDGE) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) w[u][v] = EB[ry[u] * L::BW + rx[v]];
+            } else {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const F4 t = ((const F4*)(EB + ry[u] * L::BW + tx))[v];
+                    w[u][4 * v] = t.x; w[u][4 * v + 1] = t.y; w[u][4 * v + 2] = t.z; w[u][4 * v + 3] = t.w;
+                }
+            }
+        }
+        median25_block2x4(w, mb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int dy = k >> 2, dx = k & 3;
+            if (EDGE) { if (x + dx >= W) continue; }          // W is even, not necessarily a multiple of 4
+            int o = (ty + dy) * TW + tx + dx;
+            float r1 = RP[o], b1 = BP[o];
+            Rgb v;
+            v.r = r1; v.b = b1;
+            v.g = (((mr[k] + mb[k]) + r1) + b1) / 2.0f;
+            stage_pixel<TW, TH>(out, p.st, p.g, p.c, ty + dy, tx + dx, v);
         }
     }
 }

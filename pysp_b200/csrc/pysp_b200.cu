@@ -49,6 +49,17 @@ constexpr int K1_TW = PYSP_K1_TW, K1_TH = PYSP_K1_TH, K1_THREADS = PYSP_K1_THREA
 #define PYSP_K2_CTAS 1
 #endif
 constexpr int K2_TW = PYSP_K2_TW, K2_TH = PYSP_K2_TH, K2_THREADS = PYSP_K2_THREADS;
+// work item of the median phases: a 2x4 block of outputs (60.75 min/max per median) or a 2x2 block (67.5)
+#ifndef PYSP_K2_BLOCK4
+#define PYSP_K2_BLOCK4 1
+#endif
+#if PYSP_K2_BLOCK4
+#define PYSP_K2_PHASE_B median_phase_b4
+#define PYSP_K2_PHASE_C median_phase_c4
+#else
+#define PYSP_K2_PHASE_B median_phase_b
+#define PYSP_K2_PHASE_C median_phase_c
+#endif
 
 struct OutMaps { CUtensorMap m[3]; };     // final image: m[0]; planes: m[0..2]
 
@@ -187,16 +198,16 @@ median_stage_kernel(const __grid_constant__ MedianParams p, const __grid_constan
         if (edge) {
             median_fix_border<K2_TW, K2_TH>(p, smem, tile_x, tile_y);
             __syncthreads();
-            median_phase_b<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
+            PYSP_K2_PHASE_B<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
         } else {
-            median_phase_b<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
+            PYSP_K2_PHASE_B<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
         }
         if (p.st.tma && threadIdx.x == 0) tma_store_wait_read();     // previous tile's store has read the staging tile
         __syncthreads();                                             // input planes consumed
         const int next = tile + gridDim.x;
         if (p.tma_in && next < p.n_tiles) fetch(next);
-        if (edge) median_phase_c<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
-        else median_phase_c<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
+        if (edge) PYSP_K2_PHASE_C<K2_TW, K2_TH, true>(p, smem, tile_x, tile_y);
+        else PYSP_K2_PHASE_C<K2_TW, K2_TH, false>(p, smem, tile_x, tile_y);
         if (p.st.tma) fence_async_smem();
         __syncthreads();
         store_tile<K2_TW, K2_TH>((const float*)(smem + L::OFF_OUT), p.st, p.g, out_maps, tile_x * K2_TW,

@@ -58,13 +58,15 @@ static void run_chain(const DevelopPlan& plan) {
             poison();
             const int bx = tx * TW2 - 4, by = p.y_begin + ty * TH2 - 4 - p.in_row0;
             for (int k = 0; k < 3; ++k) box_load_generic(smem + LM::OFF_IN + k * LM::PLANE_BYTES, p.in[k], bx, by, LM::AW, LM::AH);
+            // the product runs the 2x4-block phases; odd stages of the emulation run the 2x2-block ones so that both stay covered
+            const bool block4 = (s & 1) == 0;
             if (median_tile_is_edge<TW2, TH2>(p, tx, ty)) {
                 median_fix_border<TW2, TH2>(p, smem, tx, ty);
-                median_phase_b<TW2, TH2, true>(p, smem, tx, ty);
-                median_phase_c<TW2, TH2, true>(p, smem, tx, ty);
+                if (block4) { median_phase_b4<TW2, TH2, true>(p, smem, tx, ty); median_phase_c4<TW2, TH2, true>(p, smem, tx, ty); }
+                else { median_phase_b<TW2, TH2, true>(p, smem, tx, ty); median_phase_c<TW2, TH2, true>(p, smem, tx, ty); }
             } else {
-                median_phase_b<TW2, TH2, false>(p, smem, tx, ty);
-                median_phase_c<TW2, TH2, false>(p, smem, tx, ty);
+                if (block4) { median_phase_b4<TW2, TH2, false>(p, smem, tx, ty); median_phase_c4<TW2, TH2, false>(p, smem, tx, ty); }
+                else { median_phase_b<TW2, TH2, false>(p, smem, tx, ty); median_phase_c<TW2, TH2, false>(p, smem, tx, ty); }
             }
             store_tile_generic<TW2, TH2>((const float*)(smem + LM::OFF_OUT), p.st, p.g, tx * TW2, p.y_begin + ty * TH2);
         }
