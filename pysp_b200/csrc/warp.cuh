@@ -82,17 +82,18 @@ __device__ __forceinline__ float lanczos4_sample(const float* __restrict__ src, 
                                                  const float* __restrict__ tab, float mx, float my) {
     const int sx = __float2int_rn(mx * 32.0f), sy = __float2int_rn(my * 32.0f);     // cvRound: half to even
     const int ix = (sx >> 5) - 3, iy = (sy >> 5) - 3;
-    const float* wx = tab + (sx & 31) * 8;
-    const float* wy = tab + (sy & 31) * 8;
+    // the shared-memory copy of the table is transposed ([tap][fraction]): lanes with different fractions hit different banks
+    const float* wx = tab + (sx & 31);
+    const float* wy = tab + (sy & 31);
     float hx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hx[i] = wx[i];
+    for (int i = 0; i < 8; ++i) hx[i] = wx[i * 32];
     float sum = 0.0f;
     if (ix >= 0 && ix + 8 <= W && iy >= 0 && iy + 8 <= H) {
         const float* p = src + (long long)iy * pitch_f + (long long)ix * step;
 #pragma unroll
         for (int r = 0; r < 8; ++r, p += pitch_f) {
-            const float vy = wy[r];
+            const float vy = wy[r * 32];
             float row = __ldg(p) * (vy * hx[0]);
 #pragma unroll
             for (int c = 1; c < 8; ++c) row = row + __ldg(p + c * step) * (vy * hx[c]);
@@ -103,7 +104,7 @@ __device__ __forceinline__ float lanczos4_sample(const float* __restrict__ src, 
         for (int r = 0; r < 8; ++r) {
             const int yy = iy + r;
             if (yy < 0 || yy >= H) continue;
-            const float vy = wy[r];
+            const float vy = wy[r * 32];
             const float* p = src + (long long)yy * pitch_f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) warp_table_kernel(const WarpTableParams p
 // cv2.remap of one plane through a table held in HBM (the reference's two-step form)
 __global__ void __launch_bounds__(256) remap_lanczos4_kernel(const RemapParams p) {
     __shared__ float tab[256];
-    tab[threadIdx.x] = p.tab[threadIdx.x];
+    tab[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] = p.tab[threadIdx.x];      // [32][8] -> [8][32]
     __syncthreads();
     const long long n = (long long)p.H * p.W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -147,29 +148,124 @@ __global__ void __launch_bounds__(256) remap_lanczos4_kernel(const RemapParams p
     }
 }
 
+// the same sample taken from a patch of the source plane staged in shared memory: `patch` holds rows [py0, py0 + PH) and
+// columns [px0, px0 + PW) of the plane, zero outside the image (= BORDER_CONSTANT), and the caller guarantees that the 8x8
+// window lies inside the patch.  Interior windows are summed row by row, border windows tap by tap (OpenCV's two orders); a
+// zero-filled tap adds +0.0 * w, which leaves a float32 sum unchanged, so the border order over the padded patch gives the
+// bits of the tap-skipping loop.
+template <int PW>
+__device__ __forceinline__ float lanczos4_sample_smem(const float* __restrict__ patch, int px0, int py0, int H, int W,
+                                                      const float* __restrict__ tab, int sx, int sy) {
+    const int ix = (sx >> 5) - 3, iy = (sy >> 5) - 3;
+    // the shared-memory copy of the table is transposed ([tap][fraction]): lanes with different fractions hit different banks
+    const float* wx = tab + (sx & 31);
+    const float* wy = tab + (sy & 31);
+    float hx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hx[i] = wx[i * 32];
+    const float* p = patch + (iy - py0) * PW + (ix - px0);
+    float sum = 0.0f;
+    if (ix >= 0 && ix + 8 <= W && iy >= 0 && iy + 8 <= H) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r, p += PW) {
+            const float vy = wy[r * 32];
+            float row = p[0] * (vy * hx[0]);
+#pragma unroll
+            for (int c = 1; c < 8; ++c) row = row + p[c] * (vy * hx[c]);
+            sum = sum + row;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r, p += PW) {
+            const float vy = wy[r * 32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sum = sum + p[c] * (vy * hx[c]);
+        }
+    }
+    return sum;
+}
+
 // opcode_warp_rectilinear for every plane of an interleaved image in ONE kernel: the coordinates are computed in registers
 // and never written to HBM (24 B/px of algorithmic traffic for three planes instead of 72 with tables).  A block owns a
-// 32 x 8 pixel patch so that the 8x8 gather windows of neighbouring threads overlap in L1.
+// 32 x 8 pixel patch of the output; lens distortion is smooth, so the source windows of its 256 pixels cover a patch only a
+// little larger.  Per plane the block finds that bounding box (warp + block min/max of the window origins), stages it in
+// shared memory with coalesced row loads, and every thread takes its 64 taps from there (one shared-memory wavefront per
+// tap instead of three to four L1 wavefronts for a strided global gather).  A block whose box does not fit the staging
+// buffer (extreme coefficients) gathers from global memory instead: same arithmetic, same bits.
+#define PYSP_WARP_PW 56
+#define PYSP_WARP_PH 28
+#ifndef PYSP_WARP_SMEM
+#define PYSP_WARP_SMEM 1
+#endif
 __global__ void __launch_bounds__(256) warp_apply_kernel(const WarpApplyParams p) {
     __shared__ float tab[256];
-    tab[threadIdx.x] = p.tab[threadIdx.x];
+    __shared__ float patch[PYSP_WARP_MAX_PLANES * PYSP_WARP_PH * PYSP_WARP_PW];
+    __shared__ int box[2][4];
+    tab[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] = p.tab[threadIdx.x];      // [32][8] -> [8][32]
+    if (threadIdx.x < 8) box[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 2) ? -0x7fffffff : 0x7fffffff;
     __syncthreads();
     const int tiles_x = (p.g.W + 31) / 32, tiles_y = (p.g.H + 7) / 8;
     const long long pitch_f = (long long)p.g.W * p.planes;
-    for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+    int flip = 0;
+    for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x, flip ^= 1) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int x = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5);
-        if (x >= p.g.W || y >= p.g.H) continue;
-        for (int c = 0; c < p.planes; ++c) {
-            float sx = (float)x, sy = (float)y;
-            if (p.prior) {
-                const float2 s = *(const float2*)(p.prior + (((long long)y * p.g.W + x) * p.planes + c) * 2);
-                sx = s.x; sy = s.y;
+        const bool live = x < p.g.W && y < p.g.H;
+        int sxq[PYSP_WARP_MAX_PLANES], syq[PYSP_WARP_MAX_PLANES];
+        int lox = 0x7fffffff, loy = 0x7fffffff, hix = -0x7fffffff, hiy = -0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < PYSP_WARP_MAX_PLANES; ++c) {
+            sxq[c] = syq[c] = 0;
+            if (c < p.planes && live) {
+                float sx = (float)x, sy = (float)y;
+                if (p.prior) {
+                    const float2 s = *(const float2*)(p.prior + (((long long)y * p.g.W + x) * p.planes + c) * 2);
+                    sx = s.x; sy = s.y;
+                }
+                float mx, my;
+                warp_coord(p.g, p.k[c], sx, sy, &mx, &my);
+                sxq[c] = __float2int_rn(clip_coord(mx, p.g.W) * 32.0f);      // cvRound: half to even
+                syq[c] = __float2int_rn(clip_coord(my, p.g.H) * 32.0f);
+                lox = min(lox, (sxq[c] >> 5) - 3); hix = max(hix, (sxq[c] >> 5) - 3);
+                loy = min(loy, (syq[c] >> 5) - 3); hiy = max(hiy, (syq[c] >> 5) - 3);
             }
-            float mx, my;
-            warp_coord(p.g, p.k[c], sx, sy, &mx, &my);
-            p.dst[((long long)y * p.g.W + x) * p.planes + c] =
-                lanczos4_sample(p.src + c, pitch_f, p.planes, p.g.H, p.g.W, tab, clip_coord(mx, p.g.W), clip_coord(my, p.g.H));
+        }
+        bool fits = false;
+        int px0 = 0, py0 = 0;
+        if (PYSP_WARP_SMEM) {
+            // bounding box of the window origins of every live pixel and plane of the block (two alternating boxes: the one
+            // of the next tile is re-armed while this one is in use)
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o)); loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+                hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o)); hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&box[flip][0], lox); atomicMin(&box[flip][1], loy); atomicMax(&box[flip][2], hix); atomicMax(&box[flip][3], hiy);
+            }
+            __syncthreads();                                  // (also: every thread is done with the previous tile's patch)
+            px0 = box[flip][0]; py0 = box[flip][1];
+            const int pw = box[flip][2] + 8 - px0, ph = box[flip][3] + 8 - py0;
+            fits = pw <= PYSP_WARP_PW && ph <= PYSP_WARP_PH;
+            if (threadIdx.x < 4) box[flip ^ 1][threadIdx.x] = (threadIdx.x & 2) ? -0x7fffffff : 0x7fffffff;
+            if (fits) {
+                for (int i = threadIdx.x; i < ph * PYSP_WARP_PW; i += 256) {
+                    const int r = i / PYSP_WARP_PW, cc = i - r * PYSP_WARP_PW;
+                    const int yy = py0 + r, xx = px0 + cc;
+                    const bool in = cc < pw && yy >= 0 && yy < p.g.H && xx >= 0 && xx < p.g.W;
+                    const float* q = p.src + (long long)yy * pitch_f + (long long)xx * p.planes;
+                    for (int c = 0; c < p.planes; ++c) patch[c * (PYSP_WARP_PH * PYSP_WARP_PW) + i] = in ? __ldg(q + c) : 0.0f;
+                }
+            }
+            __syncthreads();                                  // patch filled; box[flip] read by everyone
+        }
+        if (live) {
+            for (int c = 0; c < p.planes; ++c) {
+                float v;
+                if (fits) v = lanczos4_sample_smem<PYSP_WARP_PW>(patch + c * (PYSP_WARP_PH * PYSP_WARP_PW), px0, py0, p.g.H, p.g.W, tab, sxq[c], syq[c]);
+                else v = lanczos4_sample(p.src + c, pitch_f, p.planes, p.g.H, p.g.W, tab, (float)sxq[c] * 0.03125f, (float)syq[c] * 0.03125f);
+                p.dst[((long long)y * p.g.W + x) * p.planes + c] = v;
+            }
         }
     }
 }

@@ -115,6 +115,14 @@ def test_identity_and_errors(eng):
     img = torch.rand((H, W, 3), device="cuda")
     out = eng.warp_rectilinear(img, [(1, 0, 0, 0, 0, 0)] * 3, (0.5, 0.5), 0.0)     # scale 0: exactly the pixel grid
     assert torch.equal(out, img)
+    # strong magnification / shear: the source windows of a block no longer fit the shared-memory patch and the kernel
+    # gathers from global memory instead -- same bits as the two-step form (table in HBM, then remap) either way
+    big = torch.rand((200, 328, 3), device="cuda")
+    for k in ((2.2, -0.3, 0.1, 0.0, 0.05, -0.04), (0.45, 0.2, 0.0, 0.0, 0.0, 0.0), (1.01, -0.02, 0.0, 0.0, 0.3, 0.25)):
+        fused = eng.warp_rectilinear(big, [k] * 3, (0.47, 0.52), 1.0)
+        for i in range(3):
+            two = eng.remap_lanczos4(big, i, eng.warp_table(200, 328, k, (0.47, 0.52), 1.0))
+            assert torch.equal(two.view(torch.int32), fused[..., i].contiguous().view(torch.int32)), k
     with pytest.raises(ValueError):
         eng.warp_rectilinear(img, [(1, 0, 0, 0, 0, 0)] * 2, (0.5, 0.5))
     with pytest.raises(ValueError):
