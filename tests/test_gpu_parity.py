@@ -244,6 +244,30 @@ def test_side_stream_is_safe(eng):
         assert torch.equal(b.view(torch.int32), want_ff.view(torch.int32))
 
 
+def test_develop_is_graph_capturable(eng):
+    """include/pysp_b200.h: after the first call on a device pysp_develop only launches kernels -- it can be captured into a
+    CUDA graph and replayed (no allocation, no synchronising call, no host-side state change on the launch path)."""
+    raw = eng.to_device(syn.scene(600, 900, 14))
+    raw2 = eng.to_device(syn.scene(600, 900, 15))
+    kw = dict(stages=2, black=syn.BLACK, white=syn.WHITE)
+    want = eng.develop(raw, WB, M, **kw)
+    want2 = eng.develop(raw2, WB, M, **kw)
+    src = raw.clone()
+    out = torch.empty_like(want)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.develop(src, WB, M, out_tensor=out, **kw)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), want.view(torch.int32))
+    src.copy_(raw2)                     # new input in the captured buffer, same graph
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), want2.view(torch.int32))
+
+
 def test_hdr_fuse(eng):
     import pysp_b200 as P
     from pysp_b200.wb_cct import CameraWhiteBalance
