@@ -394,6 +394,9 @@ static int resident_ctas(const void* kernel, int threads, int smem_bytes, int* o
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes);
     if (e != cudaSuccess) return fail(PYSP_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (per_sm < 1) return fail(PYSP_ERR_CUDA, "kernel does not fit on an SM");
+#ifdef PYSP_GRID_PER_SM            // A/B builds (tools/overlap_bench.py): fewer CTAs per SM than would fit, to leave room for another kernel
+    if (per_sm > PYSP_GRID_PER_SM) per_sm = PYSP_GRID_PER_SM;
+#endif
     *out = sms * per_sm;
     return PYSP_OK;
 }
