@@ -138,56 +138,53 @@ __global__ void __launch_bounds__(256) gamma_kernel(GammaParams p) {
         p.out[i] = srgb_gamma(p.in[i]);
 }
 
-__global__ void __launch_bounds__(256) fuse_kernel(FuseParams p) {
-    // one item = four photosites of a row (two CFA sites, alternating)
-    const RowItems ri(p.H, p.W, 4);
-    bool vec = (p.W % 4 == 0) && (p.in_pitch % 16 == 0) && (p.out_pitch % 16 == 0) && ((size_t)p.out % 16 == 0) &&
-               (!p.count || (p.count_pitch % 16 == 0 && (size_t)p.count % 16 == 0));
-    for (int k = 0; k < p.n; ++k) vec = vec && ((size_t)p.in[k] % 16 == 0);
+// raw_hdr.py:108-148.  VEC: an item is four photosites of a row (one 16-byte access per bracket and output; the host checks
+// alignment), else one photosite.  Brackets are accumulated strictly in list order; the next bracket's load is issued before
+// the current one is accumulated, the occupancy of a 32-register kernel does the rest of the latency hiding.
+template <bool VEC>
+__global__ void __launch_bounds__(256) fuse_kernel(const FuseParams p) {
+    constexpr int V = VEC ? 4 : 1;
+    const RowItems ri(p.H, p.W, V);
     PYSP_ROW_ITEMS(ri, y, c) {
-        const int x0 = (int)c * 4;
-        const int ch0 = (int)y & 1;                                    // channel of even columns: R (0) or G (1); odd: +1
-        float sum_w[4] = {0, 0, 0, 0}, sum_p[4] = {0, 0, 0, 0}, bright[4] = {0, 0, 0, 0};
-        int cnt[4] = {0, 0, 0, 0};
-        const int nv = vec ? 4 : min(4, p.W - x0);
-        for (int k0 = 0; k0 < p.n; k0 += 4) {    // four brackets' loads in flight, accumulation strictly in list order
-            float v[4][4];
+        const int x0 = (int)c * V;
+        const int ch0 = ((int)y & 1) + (VEC ? 0 : (x0 & 1));           // channel of element 0: R G / G B rows; odd elements: + 1
+        const long long off = y * p.in_pitch + (long long)x0 * 4;
+        float v[V], nx[V], sum_w[V], sum_p[V], bright[V];
+        int cnt[V];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = k0 + kk;
+        for (int j = 0; j < V; ++j) { sum_w[j] = 0.0f; sum_p[j] = 0.0f; bright[j] = 0.0f; cnt[j] = 0; }
+        if (VEC) { const float4 t = *(const float4*)((const char*)p.in[0] + off); v[0] = t.x; v[V > 1 ? 1 : 0] = t.y; v[V > 2 ? 2 : 0] = t.z; v[V > 3 ? 3 : 0] = t.w; }
+        else v[0] = *(const float*)((const char*)p.in[0] + off);
+        for (int k = 0; k < p.n; ++k) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[kk][j] = 0.0f;
-                if (k < p.n) {
-                    const float* src = (const float*)((const char*)p.in[k] + y * p.in_pitch) + x0;
-                    if (vec) { const float4 t = *(const float4*)src; v[kk][0] = t.x; v[kk][1] = t.y; v[kk][2] = t.z; v[kk][3] = t.w; }
-                    else for (int j = 0; j < nv; ++j) v[kk][j] = src[j];
-                }
+            for (int j = 0; j < V; ++j) nx[j] = v[j];
+            if (k + 1 < p.n) {
+                if (VEC) { const float4 t = *(const float4*)((const char*)p.in[k + 1] + off); nx[0] = t.x; nx[V > 1 ? 1 : 0] = t.y; nx[V > 2 ? 2 : 0] = t.z; nx[V > 3 ? 3 : 0] = t.w; }
+                else nx[0] = *(const float*)((const char*)p.in[k + 1] + off);
             }
+            const float bias0 = p.bias[k][ch0], bias1 = p.bias[k][VEC ? ch0 + 1 : ch0], ev = p.ev_off[k];
+            const bool is_bright = k == p.brightest;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = k0 + kk;
-                if (k >= p.n) break;
-                const float bias0 = p.bias[k][ch0], bias1 = p.bias[k][ch0 + 1], ev = p.ev_off[k];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float w = (0.5f - fabsf(v[kk][j] - 0.5f)) * ((j & 1) ? bias1 : bias0);     // raw_hdr.py:135-141
-                    sum_w[j] = sum_w[j] + w;
-                    sum_p[j] = sum_p[j] + ((v[kk][j] * w) * ev);
-                    cnt[j] += w > 0.0f ? 1 : 0;
-                    if (k == p.brightest) bright[j] = v[kk][j] * ev;
-                }
+            for (int j = 0; j < V; ++j) {
+                const float w = (0.5f - fabsf(v[j] - 0.5f)) * ((j & 1) ? bias1 : bias0);     // raw_hdr.py:135-141
+                sum_w[j] = sum_w[j] + w;
+                sum_p[j] = sum_p[j] + ((v[j] * w) * ev);
+                cnt[j] += w > 0.0f ? 1 : 0;
+                if (is_bright) bright[j] = v[j] * ev;
+                v[j] = nx[j];
             }
         }
-        float o[4];
+        float o[V];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float q = sum_p[j] / sum_w[j]; o[j] = (sum_w[j] == 0.0f) ? bright[j] : q; }
+        for (int j = 0; j < V; ++j) { const float q = sum_p[j] / sum_w[j]; o[j] = (sum_w[j] == 0.0f) ? bright[j] : q; }
         float* dst = (float*)((char*)p.out + y * p.out_pitch) + x0;
         int32_t* dc = p.count ? (int32_t*)((char*)p.count + y * p.count_pitch) + x0 : nullptr;
-        if (vec) {
-            *(float4*)dst = make_float4(o[0], o[1], o[2], o[3]);
-            if (dc) *(int4*)dc = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        if (VEC) {
+            *(float4*)dst = make_float4(o[0], o[V > 1 ? 1 : 0], o[V > 2 ? 2 : 0], o[V > 3 ? 3 : 0]);
+            if (dc) *(int4*)dc = make_int4(cnt[0], cnt[V > 1 ? 1 : 0], cnt[V > 2 ? 2 : 0], cnt[V > 3 ? 3 : 0]);
         } else {
-            for (int j = 0; j < nv; ++j) { dst[j] = o[j]; if (dc) dc[j] = cnt[j]; }
+            dst[0] = o[0];
+            if (dc) dc[0] = cnt[0];
         }
     }
 }

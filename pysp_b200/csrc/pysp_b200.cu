@@ -576,7 +576,11 @@ int pysp_fuse_exposures(const float* const* brackets, int32_t n, int64_t in_pitc
     }
     p.in_pitch = in_pitch; p.n = n; p.H = H; p.W = W; p.brightest = brightest;
     p.out = out; p.out_pitch = out_pitch; p.count = count; p.count_pitch = count_pitch;
-    fuse_kernel<<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    bool vec = (W % 4 == 0) && (in_pitch % 16 == 0) && (out_pitch % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+               (!count || (count_pitch % 16 == 0 && (uintptr_t)count % 16 == 0));
+    for (int i = 0; i < n; ++i) vec = vec && ((uintptr_t)brackets[i] % 16 == 0);
+    if (vec) fuse_kernel<true><<<grid_for((long long)H * (W / 4), 256), 256, 0, (cudaStream_t)stream>>>(p);
+    else fuse_kernel<false><<<grid_for((long long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("fuse_kernel");
 }
 

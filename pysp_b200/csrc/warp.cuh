@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(256) warp_apply_kernel(const WarpApplyParams p
             __syncthreads();                                  // patch filled; box[flip] read by everyone
         }
         if (live) {
-            for (int c = 0; c < p.planes; ++c) {
+#pragma unroll                                   // static plane index: sxq / syq stay in registers
+            for (int c = 0; c < PYSP_WARP_MAX_PLANES; ++c) {
+                if (c >= p.planes) break;
                 float v;
                 if (fits) v = lanczos4_sample_smem<PYSP_WARP_PW>(patch + c * (PYSP_WARP_PH * PYSP_WARP_PW), px0, py0, p.g.H, p.g.W, tab, sxq[c], syq[c]);
                 else v = lanczos4_sample(p.src + c, pitch_f, p.planes, p.g.H, p.g.W, tab, (float)sxq[c] * 0.03125f, (float)syq[c] * 0.03125f);

@@ -13,3 +13,10 @@ for _ in range(2):
     br = [sensor, flat, sensor, flat, sensor]
     engine.fuse_exposures(br, [0.25, 0.5, 1, 2, 4], np.ones((5, 3), np.float32), 4)
 torch.cuda.synchronize()
+# DNG warp and the remaining point-wise kernels
+img = engine.to_device(rng.random((H, W, 3), dtype=np.float32))
+k = [(1.0012, -0.0321, 0.0104, -0.0023, 0.0007, -0.0004)] * 3
+for _ in range(2):
+    engine.warp_rectilinear(img, k, (0.4987, 0.5021))
+    engine.bayer_plane_means(flat)
+torch.cuda.synchronize()
