@@ -124,6 +124,33 @@ PYSP_HD void store_tile_generic(const float* out, const StoreParams& st, const F
         if (st.kind == OUT_LIN_F16 || st.kind >= OUT_SRGB_U8) {
             // narrow outputs: converted on the way out of the float staging tile (consecutive threads write consecutive
             // elements of a tile row).  Quantised sRGB: round-to-nearest of the gamma-encoded value times 255 / 65535.
+            // A tile that lies inside the image with 4-byte aligned rows leaves as packed 32-bit words (four u8 or two
+            // 16-bit values per store); partial tiles and unaligned rows go element by element.
+            const int esz = out_kind_bytes(st.kind);
+            const int per = 4 / esz;                                  // elements per 32-bit word
+            static_assert((TW * 3) % 4 == 0, "a tile row is a whole number of words for every narrow kind");
+            const bool words = by >= 0 && by + TH <= st.img.rows && bx >= 0 && bx + TW * 3 <= st.img.cols &&
+                               ((long long)bx * esz) % 4 == 0 && st.img.pitch % 4 == 0 && ((uintptr_t)st.img.base % 4) == 0;
+            if (words) {
+                const int wpr = TW * 3 / per;                         // words per tile row
+                PYSP_ITEMS(i, TH * wpr) {
+                    const int r = i / wpr, wc = i - r * wpr;
+                    const float* s = out + r * (TW * 3) + wc * per;
+                    uint32_t word;
+                    if (st.kind == OUT_SRGB_U8)
+                        word = quantise(s[0], 255.0f) | (quantise(s[1], 255.0f) << 8) | (quantise(s[2], 255.0f) << 16) | (quantise(s[3], 255.0f) << 24);
+                    else if (st.kind == OUT_SRGB_U16)
+                        word = quantise(s[0], 65535.0f) | (quantise(s[1], 65535.0f) << 16);
+                    else {
+#ifndef PYSP_HOST_EMU
+                        word = (uint32_t)__half_as_ushort(__float2half_rn(s[0])) | ((uint32_t)__half_as_ushort(__float2half_rn(s[1])) << 16);
+#else
+                        word = 0;
+#endif
+                    }
+                    *(uint32_t*)((char*)st.img.base + (long long)(by + r) * st.img.pitch + (long long)bx * esz + (long long)wc * 4) = word;
+                }
+            } else
             PYSP_ITEMS(i, TH * TW * 3) {
                 int r = i / (TW * 3), cc = i - r * (TW * 3);
                 int gy = by + r, gx = bx + cc;

@@ -74,7 +74,12 @@ namespace pysp {
 
 enum InKind { IN_U16 = 0, IN_F32 = 1 };
 enum OutKind { OUT_CAM_F32 = 0, OUT_LIN_F32 = 1, OUT_LIN_F16 = 2, OUT_SRGB_U8 = 3, OUT_SRGB_U16 = 4 };
-static constexpr int out_kind_bytes(int kind) { return kind == OUT_SRGB_U8 ? 1 : ((kind == OUT_LIN_F16 || kind == OUT_SRGB_U16) ? 2 : 4); }
+#ifdef __CUDACC__
+#define PYSP_HOSTDEV __host__ __device__
+#else
+#define PYSP_HOSTDEV
+#endif
+PYSP_HOSTDEV constexpr int out_kind_bytes(int kind) { return kind == OUT_SRGB_U8 ? 1 : ((kind == OUT_LIN_F16 || kind == OUT_SRGB_U16) ? 2 : 4); }
 
 struct FrameGeom {
     int H, W;            // frame size (even); flips keep the size
