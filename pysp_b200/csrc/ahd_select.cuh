@@ -52,6 +52,8 @@ struct SelectTile {
     static constexpr int OFF_CAND = align128(OFF_LABAB + 2 * LH * LW * 4);       // [4][TH][TW] f32  RH,BH,RV,BV
     static constexpr int SMEM_BYTES = align128(OFF_CAND + 4 * TH * TW * 4);
     static constexpr int OFF_OUT = OFF_LABL;       // [3][TH][TW] f32 output tile: aliases Lab (dead after phase 3)
+    // QualityDemosaic.Fast (eag.cuh) uses the quarter planes and the output tile only
+    static constexpr int SMEM_BYTES_EAG = align128(OFF_OUT + 3 * align128(TH * TW * 4));
     static constexpr int OFF_CNT = OFF_Q + P_DHR * QN * 4;   // [CH][CW] u16 (H | V << 8): aliases the D planes (dead after phase 2)
     static_assert(TW % 4 == 0 && TH % 2 == 0 && BOXW % 8 == 0, "tile must be quad aligned and its box 16-byte granular");
     static_assert(3 * ((TH * TW * 4 + 127) / 128 * 128) <= 4 * LH * LW * 4, "output tile must fit in the Lab region");
