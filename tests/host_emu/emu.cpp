@@ -82,6 +82,7 @@ extern "C" int emu_develop(const pysp_develop_args* a, int tw, int th) {
     if (rc) return rc;
     if (old) run_chain<60, 28, 60, 60>(plan);
     else if (tw == 60 && th == 60) run_chain<60, 60>(plan);   // the product's tiles
+    else if (tw == 60 && th == 44) run_chain<60, 44>(plan);   // the K1 tile of QualityDemosaic.Fast
     else if (tw == 56 && th == 30) run_chain<56, 30>(plan);   // a box with the fixed 8-px margin (tile width 0 mod 8)
     else if (tw == 16 && th == 8) run_chain<16, 8>(plan);
     else if (tw == 20 && th == 8) run_chain<20, 8>(plan);     // tile width 4 mod 8: box margin alternates 8 / 12 px

@@ -127,7 +127,7 @@ def test_fast_quality_golden(emu, name):
     """QualityDemosaic.Fast (edge-assisted Gaussian) against the reference's golden outputs."""
     from conftest import golden
     d = golden(name)
-    for tile in ((16, 8), (20, 8), (60, 28), (60, 60)):
+    for tile in ((16, 8), (20, 8), (60, 28), (60, 60), (60, 44)):
         cam = emu_develop(emu, d["raw"], 3, str(d["pattern"]), tile=tile, out_kind=_capi.OUT_CAM_F32, quality=1)
         assert_bit_equal(cam, d["cam"], "Fast camera RGB %s" % (tile,))
         assert_bit_equal(emu_develop(emu, d["raw"], 0, str(d["pattern"]), tile=tile, quality=1), d["lin"], "Fast linear sRGB")
