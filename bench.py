@@ -435,13 +435,33 @@ def multi_gpu_workloads(torch, dist, engine, parallel, syn, dev, rank, world, wb
     # ---- one 100 MP frame over row bands; the raw halo rows are pulled out of the neighbours' HBM over NVLink ----
     try:
         frame = syn.scene(BIG_H, BIG_W, 1)
-        sb = parallel.SymmetricBand(BIG_H, BIG_W, torch.int16, stages)
-        b, e = sb.rows
-        sb.band().copy_(torch.from_numpy(frame[b:e].view(np.int16)).to(dev))
+        b, e = parallel.band_rows(BIG_H, world, rank)
+        my_rows = torch.from_numpy(frame[b:e].view(np.int16)).to(dev)
+        sb, why = None, None
+        try:                                              # NVLink-shared memory (a private torch API): agreed on by all ranks
+            sb = parallel.SymmetricBand(BIG_H, BIG_W, torch.int16, stages)
+            sb.band().copy_(my_rows)
+        except Exception as ex:
+            sb, why = None, repr(ex)[:200]
+        symmetric = all_ranks_true(sb is not None)
+        if symmetric:
+            transport = "NVLink peer-to-peer copies of raw halo rows out of symmetric memory (no NCCL kernel)"
+
+            def exchange():
+                return sb.exchange()
+        else:                                             # public-API fallback: NCCL send / recv of the halo rows
+            sb = None
+            transport = "NCCL send/recv of raw halo rows (symmetric memory unavailable: %s)" % why
+
+            def exchange():
+                held, hb = parallel.exchange_halo(my_rows, BIG_H, stages)
+                padded = engine.alloc_rows(held.shape[0], BIG_W, torch.int16, dev)       # 16-byte aligned rows for TMA
+                padded.copy_(held)
+                return padded, hb
 
         def band_step():
-            held, hb = sb.exchange()
-            return engine.develop(held, rows=sb.rows, frame_height=BIG_H, in_row0=hb, **kw)
+            held, hb = exchange()
+            return engine.develop(held, rows=(b, e), frame_height=BIG_H, in_row0=hb, **kw)
 
         out = band_step()
         whole_in = engine.to_device(frame.view(np.int16), dev, pad_pitch=True)
@@ -451,34 +471,60 @@ def multi_gpu_workloads(torch, dist, engine, parallel, syn, dev, rank, world, wb
         t1 = device_ms(lambda: engine.develop(whole_in, out_tensor=whole, **kw), reps) / reps
         del whole, out, whole_in
         t = device_ms(band_step, reps) / reps
-        tx = device_ms(lambda: sb.exchange(), reps) / reps
+        tx = device_ms(lambda: exchange(), reps) / reps
         mp = BIG_H * BIG_W / (t * 1e-3) / 1e6
         res["one_100MP_frame_row_bands"] = {
             "value": mp, "unit": "Mpix/s", "scaling": "strong", "ms_per_frame": t, "exchange_us": tx * 1e3,
             "bit_identical_to_1gpu": same, "compare": "element-wise, every rank its own band against its own whole-frame run",
-            "transport": "NVLink peer-to-peer copies of raw halo rows out of symmetric memory (no NCCL kernel)",
-            "halo_rows": parallel.halo_rows(stages), "band_rows": e - b,
+            "transport": transport, "halo_rows": parallel.halo_rows(stages), "band_rows": e - b,
             "ms_per_frame_1gpu": t1, "strong_scaling_efficiency": t1 / (world * t),
             "efficiency_vs_frame_batch": mp / (per_gpu_mpix_s * world)}
-        del sb, frame
-    except Exception as ex:                               # symmetric memory needs P2P-capable GPUs
+        del sb, frame, my_rows
+    except Exception as ex:
         res["one_100MP_frame_row_bands"] = {"error": repr(ex)[:300]}
     # ---- one 5-bracket HDR set, bracket k on rank k % world; the fuse kernel reads its operands from the owners' HBM ----
     try:
         nb = len(br)
         halo = parallel.halo_rows(stages)
-        sbr = parallel.SymmetricBrackets(H, W, nb, halo)
-        for k in range(nb):
-            if sbr.owner(k) == rank:
-                sbr.slot(k).copy_(br[k])
-        bb, be = sbr.rows
+        bb, be = parallel.band_rows(H, world, rank)
+        sbr, why = None, None
+        try:
+            sbr = parallel.SymmetricBrackets(H, W, nb, halo)
+            for k in range(nb):
+                if sbr.owner(k) == rank:
+                    sbr.slot(k).copy_(br[k])
+        except Exception as ex:
+            sbr, why = None, repr(ex)[:200]
+        symmetric = all_ranks_true(sbr is not None)
+        if symmetric:
+            transport = ("fuse_kernel loads the brackets from their owners' HBM over NVLink (symmetric memory): exchange and "
+                         "compute are one kernel")
 
-        def hdr_step():
-            sbr.ready()
-            rows, hb = sbr.views()
-            fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
-            sbr.done()
-            return engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=H, in_row0=hb)
+            def hdr_step():
+                sbr.ready()
+                rows, hb = sbr.views()
+                fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
+                sbr.done()
+                return engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=H, in_row0=hb)
+
+            def sync_only():
+                sbr.ready()
+                sbr.done()
+        else:                                             # public-API fallback: every rank receives its band's rows of every bracket
+            sbr = None
+            transport = "NCCL send/recv of the band's rows of every bracket (symmetric memory unavailable: %s)" % why
+            mine = {k: br[k] for k in range(nb) if k % world == rank}
+            like = torch.empty((0, W), dtype=torch.float32, device=dev)
+
+            def gather_rows():
+                return parallel.exchange_brackets_by_rows(mine, nb, H, halo, like=like)
+
+            def hdr_step():
+                rows, hb = gather_rows()
+                fused, _ = engine.fuse_exposures(rows, offs, bias, int(np.argmax(offs)), want_count=False)
+                return engine.develop(fused, wb, m, stages=stages, hdr=True, rows=(bb, be), frame_height=H, in_row0=hb)
+
+            sync_only = gather_rows
 
         out = hdr_step()
         # the single-GPU result of the same set (every rank holds a copy of all five brackets in `br`)
@@ -488,12 +534,12 @@ def multi_gpu_workloads(torch, dist, engine, parallel, syn, dev, rank, world, wb
         del whole, f1, out
         reps = 10
         t = device_ms(hdr_step, reps) / reps
-        tb = device_ms(lambda: (sbr.ready(), sbr.done()), reps) / reps
+        tb = device_ms(sync_only, reps) / reps
         res["one_hdr5_set_brackets_sharded"] = {
             "value": H * W / (t * 1e-3) / 1e6, "unit": "Mpix/s (output pixels)", "scaling": "strong", "ms_per_set": t,
             "bit_identical_to_1gpu": same, "compare": "element-wise, every rank its own band against its own single-GPU run",
-            "transport": "fuse_kernel loads the brackets from their owners' HBM over NVLink (symmetric memory): exchange and "
-                         "compute are one kernel", "exchange_us": 0.0, "device_barriers_us": tb * 1e3}
+            "transport": transport, "exchange_us": 0.0 if symmetric else tb * 1e3,
+            "device_barriers_us": tb * 1e3 if symmetric else None}
         del sbr
     except Exception as ex:
         res["one_hdr5_set_brackets_sharded"] = {"error": repr(ex)[:300]}
