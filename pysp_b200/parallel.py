@@ -47,6 +47,13 @@ def bind_to_gpu_numa_node(device_index):
         return None
 
 
+def _symmetric_memory_allowed():
+    """`torch.distributed._symmetric_memory` is a private torch API; PYSP_NO_SYMMETRIC_MEMORY=1 disables its use (callers
+    then take the NCCL transports `exchange_halo` / `exchange_brackets_by_rows`, which give the same bits)."""
+    if os.environ.get("PYSP_NO_SYMMETRIC_MEMORY"):
+        raise RuntimeError("symmetric memory disabled by PYSP_NO_SYMMETRIC_MEMORY")
+
+
 def frames_for_rank(n_frames, rank, world):
     """Whole-frame sharding: frame i goes to rank i % world."""
     return list(range(rank, n_frames, world))
@@ -122,6 +129,7 @@ class SymmetricBand:
     same row arithmetic through `exchange_halo` on gloo."""
 
     def __init__(self, height, width, dtype, stages, group=None, device=None):
+        _symmetric_memory_allowed()
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -174,6 +182,7 @@ class SymmetricBrackets:
     """
 
     def __init__(self, height, width, n_brackets, halo, group=None, device=None, dtype=torch.float32):
+        _symmetric_memory_allowed()
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
