@@ -268,6 +268,26 @@ def test_develop_is_graph_capturable(eng):
     assert torch.equal(out.view(torch.int32), want2.view(torch.int32))
 
 
+def test_frame_pipeline_host_buffers(eng):
+    """pysp_b200.pipeline.FramePipeline (the end-to-end batch API of bench.py): pinned host mosaics in, pinned host results
+    out, three streams in flight; every frame equals the device-resident develop, for float32 and 8-bit sRGB outputs; the
+    copies-only pass used as the bench's ceiling moves the same bytes and leaves the buffers usable."""
+    from pysp_b200.pipeline import FramePipeline
+    H, W = 480, 720
+    raws = [syn.scene(H, W, 30 + i) for i in range(7)]
+    pin_in = [torch.from_numpy(r.view(np.int16)).pin_memory() for r in raws]
+    for kind in ("lin", "srgb_u8"):
+        pipe = FramePipeline(H, W, WB, M, stages=1, black=syn.BLACK, white=syn.WHITE, out=kind)
+        pin_out = [pipe.pinned_output() for _ in raws]
+        pipe.run(pin_in, pin_out)
+        pipe.run_copies_only(pin_in, pin_out)            # overwrites the outputs with whatever the device buffers hold
+        pipe.run(pin_in, pin_out)
+        assert pipe.h2d_bytes() == H * W * 2 and pipe.d2h_bytes() == H * W * 3 * (4 if kind == "lin" else 1)
+        for r, o in zip(raws, pin_out):
+            want = eng.develop(eng.to_device(r), WB, M, stages=1, black=syn.BLACK, white=syn.WHITE, out=kind)
+            assert torch.equal(o.cuda(), want), kind
+
+
 def test_hdr_fuse(eng):
     import pysp_b200 as P
     from pysp_b200.wb_cct import CameraWhiteBalance
