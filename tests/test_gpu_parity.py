@@ -78,6 +78,33 @@ def test_patterns(eng, pattern):
     assert_bit_equal(gpu_develop(eng, raw, 1, pattern, (500, 510, 520, 530), (16383, 16000, 15800, 16100)), lin, pattern)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_ragged_frames_and_bands(eng, seed):
+    """Seeded random cases on the GPU: ragged even frame sizes (4x4 upwards, widths that are 2 mod 4 or not 16-byte rows,
+    partial tiles on both axes), every CFA pattern, per-site levels, 0-3 stages, a random split into row bands -- the whole
+    frame against the oracle, every band (developed from its rows + halo only) against the whole frame."""
+    rng = np.random.default_rng(300 + seed)
+    H, W = 2 * int(rng.integers(2, 150)), 2 * int(rng.integers(2, 170))
+    stages = int(rng.integers(0, 4))
+    pattern = ("RGGB", "BGGR", "GRBG", "GBRG")[int(rng.integers(0, 4))]
+    black = tuple(int(v) for v in rng.integers(400, 600, 4))
+    white = tuple(int(v) for v in rng.integers(15000, 16384, 4))
+    raw = syn.random_mosaic(H, W, 400 + seed) if seed % 3 == 0 else syn.scene(H, W, 400 + seed)
+    lin, _ = sp.develop(raw, black, white, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages, pattern)
+    what = "%dx%d %s stages=%d" % (H, W, pattern, stages)
+    assert_bit_equal(gpu_develop(eng, raw, stages, pattern, black, white), lin, what)
+    padded = eng.develop(eng.to_device(raw, pad_pitch=True), WB, M, stages=stages, pattern=pattern, black=black, white=white)
+    assert_bit_equal(padded.cpu().numpy(), lin, what + " (padded pitch)")
+    cuts = sorted(set([0, H] + [2 * int(v) for v in rng.integers(1, H // 2, size=min(3, H // 2 - 1))])) if H > 4 else [0, H]
+    halo = 6 + 4 * stages
+    for rb, re in zip(cuts[:-1], cuts[1:]):
+        r0, r1 = max(0, rb - halo), min(H, re + halo)
+        t = eng.to_device(np.ascontiguousarray(raw[r0:r1]))
+        band = eng.develop(t, WB, M, stages=stages, pattern=pattern, black=black, white=white, rows=(rb, re), frame_height=H,
+                           in_row0=r0)
+        assert_bit_equal(band.cpu().numpy(), lin[rb:re], what + " band [%d,%d)" % (rb, re))
+
+
 def test_random_noise_frame(eng):
     raw = syn.random_mosaic(256, 384, 5)      # white noise: every direction vote is contested
     lin, _ = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 1)

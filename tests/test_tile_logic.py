@@ -97,6 +97,30 @@ def test_row_bands_equal_whole_frame(emu, stages, pattern):
         assert_bit_equal(band, whole[rb:re], "band [%d,%d)" % (rb, re))
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_ragged_frames_and_bands(emu, seed):
+    """Seeded random cases: ragged even frame sizes (down to 4x4, widths that are 2 mod 4, not multiples of any tile size),
+    every CFA pattern, per-site levels, 0-3 stages, random tile size and a random split into row bands -- whole frame
+    against the oracle, every band against the whole frame."""
+    rng = np.random.default_rng(100 + seed)
+    H, W = 2 * int(rng.integers(2, 50)), 2 * int(rng.integers(2, 60))
+    stages = int(rng.integers(0, 4))
+    pattern = ("RGGB", "BGGR", "GRBG", "GBRG")[int(rng.integers(0, 4))]
+    black = tuple(int(v) for v in rng.integers(400, 600, 4))
+    white = tuple(int(v) for v in rng.integers(15000, 16384, 4))
+    tile = ((16, 8), (20, 8), (60, 28), (60, 60), (56, 30))[int(rng.integers(0, 5))]
+    raw = syn.random_mosaic(H, W, 200 + seed) if seed % 3 == 0 else syn.scene(H, W, 200 + seed)
+    lin, _ = sp.develop(raw, black, white, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, stages, pattern)
+    whole = emu_develop(emu, raw, stages, pattern, tile=tile, black=black, white=white)
+    assert_bit_equal(whole, lin, "%dx%d %s stages=%d tile=%s" % (H, W, pattern, stages, tile))
+    cuts = sorted(set([0, H] + [2 * int(v) for v in rng.integers(1, H // 2, size=min(3, H // 2 - 1))])) if H > 4 else [0, H]
+    halo = 6 + 4 * stages
+    for rb, re in zip(cuts[:-1], cuts[1:]):
+        r0, r1 = max(0, rb - halo), min(H, re + halo)
+        band = emu_develop(emu, raw, stages, pattern, tile=tile, black=black, white=white, band=(rb, re), held=(r0, r1 - r0))
+        assert_bit_equal(band, whole[rb:re], "band [%d,%d) of %dx%d" % (rb, re, H, W))
+
+
 def test_hdr_and_f32_input(emu):
     rng = np.random.default_rng(9)
     sensor = (syn.scene(32, 44, 9).astype(np.float32) / 16383.0) * np.where(rng.random((32, 44)) < 0.2, 3.0, 1.0)
