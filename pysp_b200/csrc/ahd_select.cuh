@@ -275,6 +275,8 @@ PYSP_D void select_phase0(const SelectParams& p, char* __restrict__ smem, int ti
     constexpr int BW2 = L::BOXW / 2;                          // site pairs per box row
     PYSP_ITEMS(it, QN) {
         int qy = it / QW, qx = it - qy * QW;
+        // rows beyond the band's last row + halo are never read (a tile that overhangs the end of a row band is an EDGE tile)
+        if (EDGE) { if (by0 + 2 * qy >= p.y_end + L::HY) continue; }
         float v[4];
         if (!EDGE) {
             // the two sites of a mosaic row are adjacent in the staging box (also when mirrored): one 32/64-bit load
@@ -342,7 +344,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
             int i = gy + IY - 2, j = gx + JX - 2;      // local quarter index
             if (EDGE) {
                 int fi = qy0 + i, fj = qx0 + j;
-                if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue;
+                if (fi < 0 || fi >= hq || fj < 0 || fj >= wq || 2 * fi >= p.y_end + 4) continue;
             }
             int c = i * QW + j;
             const float* R = Q + L::P_R * QN; const float* G1 = Q + L::P_G1 * QN;
@@ -369,7 +371,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
             int py = it / PW, px = it - py * PW;
             int i = py + IY - 1, j = px + JX - 1;      // local quarter index
             int fi = qy0 + i, fj = qx0 + j;            // frame quarter index
-            if (EDGE) { if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue; }
+            if (EDGE) { if (fi < 0 || fi >= hq || fj < 0 || fj >= wq || 2 * fi >= p.y_end + 2) continue; }
             // local quarter row/col of the 3 neighbours under quarter-grid REFLECT_101
             int ri[3], cj[3];
 #pragma unroll
@@ -506,6 +508,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
         PYSP_ROW_ITEMS32(by, bx, BH, BW) {
             int cy = 2 * by, cx = 2 * bx;                 // count-region coords of the block's top-left pixel
             int fy = y0 - 1 + cy, fx = x0 - 1 + cx;       // frame coords
+            if (EDGE) { if (fy >= p.y_end + 1) continue; }        // counts are needed for the band's rows + 1 only
             // Lab-region local coords of the 4x4 window (edge-duplicated at the frame border, ahd.py:64)
             int wy[4], wx[4];
 #pragma unroll
@@ -613,7 +616,7 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
         PYSP_ROW_ITEMS32(oy, ox, OH, OW) {
             int ty = 2 * oy, tx = 2 * ox;                 // tile coords of the quad
             int fy = y0 + ty, fx = x0 + tx;
-            if (EDGE) { if (fy >= H || fx >= W) continue; }       // partial tile (even dims: whole quad in or out)
+            if (EDGE) { if (fy >= p.y_end || fx >= W) continue; } // partial tile (even dims: whole quad in or out; y_end <= H)
             uint32_t w0[4], w1[4];                        // per window row: cells (0,1) and (2,3)
             if (EDGE) {
                 int wy[4], wx[4];
@@ -674,7 +677,8 @@ PYSP_D void select_phases(const SelectParams& p, char* __restrict__ smem, int ti
 template <int TW, int TH>
 PYSP_HD bool select_tile_is_edge(const SelectParams& p, int tile_x, int tile_y) {
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
-    return x0 < 6 || y0 < 6 || x0 + TW + 6 > p.g.W || y0 + TH + 6 > p.g.H;
+    // frame borders, and tiles that overhang the end of the row range (the EDGE code skips the rows nobody needs)
+    return x0 < 6 || y0 < 6 || x0 + TW + 6 > p.g.W || y0 + TH + 6 > p.g.H || y0 + TH > p.y_end;
 }
 
 }  // namespace pysp

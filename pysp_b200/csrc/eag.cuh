@@ -39,7 +39,7 @@ PYSP_D void eag_phases(const SelectParams& p, char* __restrict__ smem, int tile_
             int i = gy + IY - 1, j = gx + JX - 1;
             if (EDGE) {
                 int fi = qy0 + i, fj = qx0 + j;
-                if (fi < 0 || fi >= hq || fj < 0 || fj >= wq) continue;
+                if (fi < 0 || fi >= hq || fj < 0 || fj >= wq || 2 * fi >= p.y_end + 2) continue;
             }
             int c = i * QW + j;
             const float* G1 = Q + L::P_G1 * QN; const float* G2 = Q + L::P_G2 * QN;
@@ -62,7 +62,7 @@ PYSP_D void eag_phases(const SelectParams& p, char* __restrict__ smem, int tile_
             int oy = it / OW, ox = it - oy * OW;
             int i = oy + IY, j = ox + JX;
             int fi = qy0 + i, fj = qx0 + j;
-            if (EDGE) { if (fi >= hq || fj >= wq) continue; }
+            if (EDGE) { if (fi >= hq || fj >= wq || 2 * fi >= p.y_end) continue; }
             int ri[3], cj[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {

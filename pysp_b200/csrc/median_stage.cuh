@@ -38,7 +38,7 @@ struct MedianTile {
 template <int TW, int TH>
 PYSP_HD bool median_tile_is_edge(const MedianParams& p, int tile_x, int tile_y) {
     const int x0 = tile_x * TW, y0 = p.y_begin + tile_y * TH;
-    return x0 < 4 || y0 < 4 || x0 + TW + 4 > p.g.W || y0 + TH + 4 > p.g.H;
+    return x0 < 4 || y0 < 4 || x0 + TW + 4 > p.g.W || y0 + TH + 4 > p.g.H || y0 + TH > p.y_end;
 }
 
 // phase A (edge tiles only): the box arrives zero-filled outside the frame; REPLICATE needs the value of the
@@ -78,7 +78,7 @@ PYSP_D void median_phase_b(const MedianParams& p, char* __restrict__ smem, int t
         int by = it / NBX, bx = it - by * NBX;
         int ly = 2 * by, lx = 2 * bx;                       // region-B coords of the block's top-left pixel
         int y = y0 - 2 + ly, x = x0 - 2 + lx;
-        if (EDGE) { if (y < 0 || y >= H || x < 0 || x >= W) continue; }     // even origin, even frame: all in or all out
+        if (EDGE) { if (y < 0 || y >= H || x < 0 || x >= W || y >= p.y_end + 2) continue; }     // even origin, even frame: all in or all out
         // the input planes hold the REPLICATE extension, so the windows of in-frame pixels are final
         float w[6][6], mr[4], mb[4];
         const int c = ly * L::AW + lx;                      // input-plane index of window cell (0,0) = pixel (y-2, x-2)
@@ -129,7 +129,7 @@ PYSP_D void median_phase_b4(const MedianParams& p, char* __restrict__ smem, int 
         int by = it / NBX, bx = it - by * NBX;
         int ly = 2 * by, lx = 4 * bx;                       // region-B coords of the block's top-left pixel
         int y = y0 - 2 + ly, x = x0 - 2 + lx;
-        if (EDGE) { if (y < 0 || y >= H || x + 3 < 0 || x >= W) continue; }     // the whole block outside the frame
+        if (EDGE) { if (y < 0 || y >= H || x + 3 < 0 || x >= W || y >= p.y_end + 2) continue; }     // the whole block outside the frame / band
         float w[6][8], mr[8], mb[8];
         const int c = ly * L::AW + lx;                      // input-plane index of window cell (0,0) = pixel (y-2, x-2)
 #pragma unroll
@@ -185,7 +185,7 @@ PYSP_D void median_phase_c4(const MedianParams& p, char* __restrict__ smem, int 
         int by = it / NBX, bx = it - by * NBX;
         int ty = 2 * by, tx = 4 * bx;
         int y = y0 + ty, x = x0 + tx;
-        if (EDGE) { if (y >= H || x >= W) continue; }
+        if (EDGE) { if (y >= p.y_end || x >= W) continue; }
         int ry[6], rx[8];                                   // region-B rows/cols of the 6x8 window (REPLICATE at the frame border)
 #pragma unroll
         for (int k = 0; k < 6; ++k) ry[k] = EDGE ? clampi(y + k - 2, H) - (y0 - 2) : ty + k;
@@ -248,7 +248,7 @@ PYSP_D void median_phase_c(const MedianParams& p, char* __restrict__ smem, int t
         int by = it / NBX, bx = it - by * NBX;
         int ty = 2 * by, tx = 2 * bx;
         int y = y0 + ty, x = x0 + tx;
-        if (EDGE) { if (y >= H || x >= W) continue; }
+        if (EDGE) { if (y >= p.y_end || x >= W) continue; }
         int ry[6], rx[6];                                   // region-B rows/cols of the 6x6 window (REPLICATE at the frame border)
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
