@@ -108,6 +108,13 @@ def cpu_develop_fn(threads):
     from pysp_b200 import synthetic as syn
     cv2.setNumThreads(threads)
     try:
+        # torchrun exports OMP_NUM_THREADS=1 and NumPy's OpenBLAS read it when NumPy was imported: give the float64 matrix
+        # products of the reference (np.dot, colorize/transform.py:52) every host thread back, as in a plain `python` run
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
+    try:
         from oracle import ref_harness as rh
         if not rh.available():
             raise RuntimeError("the reference install baseline/_ref/pySP is not in this snapshot "
