@@ -110,6 +110,8 @@ def to_device(a, device=None, dtype=None, pad_pitch=False):
         return dst
     if not t.is_cuda:
         t = t.to(device if device is not None else "cuda", non_blocking=True)
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t                                     # a row-padded 2-D view stays as it is (every 2-D entry point takes a pitch)
     return t.contiguous()
 
 

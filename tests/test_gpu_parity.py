@@ -493,3 +493,20 @@ def test_repeatability_under_load(eng):
     torch.cuda.synchronize()
     vals = [int(s.item()) for s in sums]
     assert len(set(vals[0::2])) == 1 and len(set(vals[1::2])) == 1, vals
+
+
+def test_padded_mosaic_through_containers(eng):
+    """A mosaic whose rows are not 16-byte multiples (width 2 mod 8) is uploaded into a row-padded buffer by from_mosaic and
+    stays padded through RawBayerData.demosaic / develop (TMA path); results equal the oracle."""
+    import pysp_b200 as P
+    from pysp_b200.wb_cct import CameraWhiteBalance
+    raw = syn.scene(122, 202 + 8 * 3, 17)[:, :202]           # 202 x 2 B = 404 B rows
+    raw = np.ascontiguousarray(raw)
+    wb = CameraWhiteBalance(syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ)
+    img = P.RawRgbgDataFromRaw.from_mosaic(raw, list(syn.BLACK), list(syn.WHITE), P.BayerPattern.Rggb, wb, ev=10.0)
+    assert img._counts.stride(0) * 2 % 128 == 0 and img._counts.shape == (122, 202)
+    lin, cam = sp.develop(raw, syn.BLACK, syn.WHITE, WB, syn.MAT_XYZ_TO_CAM, syn.WHITE_XYZ, 1)
+    assert_bit_equal(img.demosaic(P.QualityDemosaic.Best).image, cam, "camera RGB from a padded mosaic")
+    assert_bit_equal(img.develop(1), lin, "fused develop from a padded mosaic")
+    sensor = P.bayer_normalize(torch.from_numpy(raw.view(np.int16)).cuda(), list(syn.BLACK), list(syn.WHITE))
+    assert_bit_equal(sensor.cpu().numpy(), sp.normalize(raw, syn.BLACK, syn.WHITE), "bayer_normalize")
